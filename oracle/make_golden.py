@@ -1,0 +1,85 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.pt by running the reference's own X3 module.
+
+Run in the build container (needs /root/reference):   python -m oracle.make_golden
+Weights and inputs are NOT stored: they are regenerated from oracle/synth.py by seed / clip index, so the
+fixtures hold only the reference outputs (a few hundred KB).  Each file records the recipe that produced it.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import torch
+
+from . import ref_loader, synth
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+
+def _ref_model(cfg, seed):
+    tr = dict(depth=cfg['depth'], dim=cfg['dim'], dim_text=cfg['dim_text'], dim_frames=cfg['dim_frames'],
+              heads=cfg['heads'], dim_head=cfg['dim_head'], max_seq_len=cfg['max_seq_len'], if_text_modules=True,
+              if_cross_attn=True, if_audio_conv=True, if_text_conv=True)
+    m = ref_loader.build_reference_model(tr, num_channels=cfg['num_channels'])
+    sd = synth.random_state_dict(**cfg, seed=seed)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith('video2roll_net') for k in missing), (missing, unexpected)
+    return m
+
+
+def _velocity(m, bt, t, drop):
+    """One reference transformer_with_pred_head call (X3:1993) with both drops on or off."""
+    import contextlib, io
+    m.encode_text = lambda prompt: (bt['ctx'].clone(), bt['ctx_mask'].clone())
+    b, n, _ = bt['y0'].shape
+    mask = torch.arange(n)[None, :] < bt['lens'][:, None]
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        return m.transformer_with_pred_head(
+            bt['y0'].clone(), None, times=torch.tensor(t), mask=mask, text=bt['clip'].clone(),
+            frames_embed=bt['frames'].clone(), prompt=['x'] * b, video_drop_prompt=[False] * b,
+            drop_audio_cond=drop, drop_text_cond=drop, drop_text_prompt=drop)
+
+
+def tiny():
+    cfg, seed = synth.TINY, 0
+    m = _ref_model(cfg, seed)
+    rec = dict(arch=cfg, weight_seed=seed, clips=[0, 1, 2], n=50, lens=[50, 37, 44], nc_list=[8, 5, 6],
+               live_frames=True, steps=6, cfg_strength=2.0, t_single=0.37)
+    bt = synth.batch(rec['clips'], rec['n'], lens=rec['lens'], nc_list=rec['nc_list'], dim_text=cfg['dim_text'],
+                     dim=cfg['dim'], d=cfg['num_channels'], live_frames=True)
+    out = dict(recipe=rec)
+    kw = dict(y0=bt['y0'], clip=bt['clip'], ctx=bt['ctx'], ctx_mask=bt['ctx_mask'], frames_embed=bt['frames'],
+              lens=bt['lens'], steps=rec['steps'], cfg_strength=rec['cfg_strength'])
+    out['sample_cfg'] = ref_loader.reference_sample(m, remove_parallel_component=False, **kw)
+    out['sample_apg'] = ref_loader.reference_sample(m, remove_parallel_component=True, **kw)
+    out['pred_cond'] = _velocity(m, bt, rec['t_single'], False)
+    out['pred_null'] = _velocity(m, bt, rec['t_single'], True)
+    out = {k: (v.clone().contiguous() if torch.is_tensor(v) else v) for k, v in out.items()}
+    torch.save(out, os.path.join(OUT, 'tiny_x3.pt'))
+    print('tiny_x3.pt', {k: tuple(v.shape) for k, v in out.items() if torch.is_tensor(v)})
+
+
+def shipped():
+    cfg, seed = synth.SHIPPED, 0
+    torch.set_num_threads(os.cpu_count())
+    m = _ref_model(cfg, seed)
+    rec = dict(arch=cfg, weight_seed=seed, clips=[0], n=750, lens=[750], nc_list=[8], live_frames=False, steps=3,
+               cfg_strength=2.0, t_single=0.3)
+    bt = synth.batch(rec['clips'], rec['n'], nc=8)
+    out = dict(recipe=rec)
+    t0 = time.time()
+    out['pred_cond'] = _velocity(m, bt, rec['t_single'], False)
+    out['pred_null'] = _velocity(m, bt, rec['t_single'], True)
+    out['sample_cfg'] = ref_loader.reference_sample(
+        m, y0=bt['y0'], clip=bt['clip'], ctx=bt['ctx'], ctx_mask=bt['ctx_mask'], lens=bt['lens'], steps=rec['steps'],
+        cfg_strength=rec['cfg_strength'], remove_parallel_component=False)
+    print(f'shipped: 6 reference forwards in {time.time() - t0:.1f}s')
+    out = {k: (v.clone().contiguous() if torch.is_tensor(v) else v) for k, v in out.items()}
+    torch.save(out, os.path.join(OUT, 'shipped_x3.pt'))
+    print('shipped_x3.pt', {k: tuple(v.shape) for k, v in out.items() if torch.is_tensor(v)})
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    tiny()
+    shipped()
