@@ -1,0 +1,96 @@
+/* libe2b -- C-ABI of the B200-native CFM sampling path (E2TTS.sample -> E2 Transformer).
+ *
+ * This is the boundary a reference maintainer binds instead of the PyTorch-eager code in
+ * src/e2_tts_pytorch/e2_tts_crossatt3.py ("X3").  Plain pointers and sizes only; every pointer named `dev` is a CUDA
+ * device pointer owned by the caller (torch tensors on the host side), `host` pointers are ordinary host memory.
+ * All calls are asynchronous on the given stream unless stated; none allocates after e2b_prepare().
+ * Every function returns 0 on success and a negative value on error (message: e2b_last_error).
+ *
+ * Reference interface each entry point replaces:
+ *   e2b_create / e2b_load_weights   E2TTS.__init__ + load_state_dict            X3:1275-1523, inference_v2a.py:117-124
+ *   e2b_prepare / e2b_set_conditions  the step-invariant part of sample():       X3:2162-2216 (masks, frames_embed,
+ *                                     proj_frames X3:2069, T5 context K/V of every attn2 X3:1131, CLIP stream X3:2040)
+ *   e2b_forward                     transformer_with_pred_head for all guidance passes   X3:1993-2088
+ *   e2b_transformer_forward         Transformer.forward                                  X3:941-1143
+ *   e2b_guided_euler                cfg_transformer_with_pred_head combine + project + one torchdiffeq Euler update
+ *                                   X3:2090-2113, 162-173, 2255
+ *   e2b_sample                      the odeint loop of E2TTS.sample                      X3:2221-2256
+ *   e2b_melspec                     MelSpec.forward                                      X3:375-417
+ */
+#ifndef E2B_H_
+#define E2B_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct e2b_handle e2b_handle;
+typedef void* e2b_stream;      /* cudaStream_t */
+
+typedef struct e2b_config {
+  int depth, dim, dim_text, dim_frames;
+  int heads, dim_head, frames_heads;      /* dim_head must be 64 */
+  int num_channels, num_registers, kernel_size, notes, max_seq_len;
+  int ff_mult;
+} e2b_config;
+
+typedef struct e2b_tensor {
+  const char* name;            /* reference state-dict key, e.g. "transformer.layers.0.0.3.to_q.weight" */
+  const float* dev;            /* fp32, contiguous, device */
+  int ndim;
+  long long shape[4];
+} e2b_tensor;
+
+/* pass flags: which conditions a guidance pass drops (pass 0 must be 0 = full conditioning) */
+enum { E2B_DROP_CLIP = 1, E2B_DROP_CTX = 2, E2B_DROP_ROLL = 4 };
+
+int e2b_create(const e2b_config* cfg, e2b_handle** out);
+void e2b_destroy(e2b_handle* h);
+const char* e2b_last_error(e2b_handle* h);   /* h may be NULL: last error of the calling thread */
+
+/* Copies + repacks (bf16, fused QKV+gate, GEGLU interleave, transposed conv taps) into library-owned memory. */
+int e2b_load_weights(e2b_handle* h, const e2b_tensor* tensors, int n, e2b_stream stream);
+
+/* Workspace for B clips of n frames, nc context tokens (padded length) and P guidance passes (1 + K). */
+int e2b_prepare(e2b_handle* h, int B, int n, int nc, int P);
+
+/* Step-invariant inputs.  clip_dev [B,n,dim_text], roll_dev [B,n,notes] (NULL = zeros), ctx_dev [B,nc,dim];
+ * lens_host[B] valid frames per clip, ctx_lens_host[B] valid context tokens, pass_flags_host[P]. */
+int e2b_set_conditions(e2b_handle* h, const float* clip_dev, const float* roll_dev, const float* ctx_dev,
+                       const int* lens_host, const int* ctx_lens_host, const int* pass_flags_host, e2b_stream stream);
+
+/* pred_dev [P,B,n,num_channels] = velocity of every pass at time t for state x_dev [B,n,num_channels]. */
+int e2b_forward(e2b_handle* h, const float* x_dev, float t, float* pred_dev, e2b_stream stream);
+
+/* y_dev [B,n,num_channels] is advanced over the grid t_grid_host[0..steps-1] (steps-1 Euler updates):
+ *   v = p0 + sum_k w[k] (p0 - p_k)   (apg: the single cfg update is projected orthogonal to p0, keep_parallel) */
+int e2b_sample(e2b_handle* h, float* y_dev, const float* t_grid_host, int steps, const float* guidance_w_host,
+               int apg, float keep_parallel, e2b_stream stream);
+
+/* Transformer.forward: x [b,n,dim] (already projected), times_host[b], lens_host[b], text_embed [b,n,dim_text],
+ * frames_embed [b,n,dim_frames] (already projected), ctx [b,nc,dim] -> out [b,n,dim] fp32.  Uses the workspace of
+ * e2b_prepare(B=b, n, nc, P=1). */
+int e2b_transformer_forward(e2b_handle* h, const float* x_dev, const float* times_host, const int* lens_host,
+                            const float* text_dev, const float* frames_dev, const float* ctx_dev,
+                            const int* ctx_lens_host, float* out_dev, e2b_stream stream);
+
+/* One fused guided Euler update on caller-owned buffers (pred_dev [P,B,per_sample]). scratch_dev: 2*B doubles for apg. */
+int e2b_guided_euler(float* y_dev, const float* pred_dev, int P, int B, long long per_sample, const float* w_host,
+                     float dt, int apg, float keep_parallel, double* scratch_dev, e2b_stream stream);
+
+/* wav_dev [B,nw] -> out_dev [B,n_mels,nw/hop+1] = log(clamp(mel(|STFT|), 1e-5)); tables are caller-provided device
+ * arrays: window[n_fft], fb[n_fft/2+1, n_mels] (torchaudio melscale_fbanks layout). */
+int e2b_melspec(const float* wav_dev, int B, int nw, int n_fft, int hop, int n_mels, const float* window_dev,
+                const float* fb_dev, float* out_dev, e2b_stream stream);
+
+/* algorithmic FLOPs of one e2b_forward at the prepared shape as executed (skipped null-pass attn2 not counted) */
+double e2b_forward_flops(e2b_handle* h);
+/* number of kernels launched by this library since the handle was created */
+long long e2b_launch_count(e2b_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E2B_H_ */

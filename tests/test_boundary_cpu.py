@@ -1,0 +1,99 @@
+"""Host-side checks that need no GPU: the C-ABI library builds/loads and exports every symbol include/e2b.h declares, the
+drop-in classes keep the reference's names / kwargs / state-dict keys, and the product path refuses to run without CUDA
+(there is no CPU fallback)."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def libpath():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'video-to-audio-and-piano-rp_b200'))
+    import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    hdr = open(os.path.join(ROOT, 'include', 'e2b.h')).read()
+    declared = set(re.findall(r'\b(e2b_[a-z_0-9]+)\s*\(', hdr))
+    assert {'e2b_create', 'e2b_load_weights', 'e2b_prepare', 'e2b_set_conditions', 'e2b_forward', 'e2b_sample',
+            'e2b_transformer_forward', 'e2b_guided_euler', 'e2b_melspec', 'e2b_last_error', 'e2b_destroy'} <= declared
+    lib = ctypes.CDLL(libpath)
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/e2b.h but not exported'
+    from e2_tts_pytorch import _lib
+    for name in _lib.EXPORTED_SYMBOLS:
+        assert hasattr(lib, name), name
+
+
+def test_library_is_sm100a_tcgen05_tma(libpath):
+    """SASS evidence: UTC*MMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG (TMA) -- and no legacy HMMA path."""
+    import shutil, subprocess
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    sass = subprocess.run([cuobjdump, '-sass', libpath], capture_output=True, text=True).stdout
+    assert 'sm_100a' in sass
+    assert re.search(r'UTC\w*MMA', sass) and 'LDTM' in sass and 'UTMALDG' in sass
+    assert not re.search(r'\bHMMA\b', sass)
+
+
+def test_state_dict_keys_match_reference_names():
+    from e2_tts_pytorch.e2_tts_crossatt3 import E2TTS
+    cfg = synth.TINY
+    m = E2TTS(transformer=dict(depth=cfg['depth'], dim=cfg['dim'], dim_text=cfg['dim_text'], dim_frames=cfg['dim_frames'],
+                               heads=cfg['heads'], dim_head=64, max_seq_len=cfg['max_seq_len'], if_text_conv=True),
+              duration_predictor=None, if_cond_proj_in=False, if_embed_text=False, if_text_encoder2=False, if_clip_encoder=False,
+              num_channels=cfg['num_channels'], sampling_rate=24000, audiocond_drop_prob=1.1, cond_drop_prob=-0.1,
+              prompt_drop_prob=-0.1, tokenizer='phoneme_zh')
+    ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    ref = {k: tuple(v.shape) for k, v in synth.random_state_dict(**cfg).items()}     # pinned against X3 in test_oracle_vs_reference
+    assert ours == ref
+    assert m.num_channels == cfg['num_channels'] and m.sampling_rate == 24000 and m.vocos is None
+    # default init keeps the reference's dead-at-init groups
+    sd = m.state_dict()
+    assert torch.count_nonzero(sd['transformer.layers.0.0.2.to_gamma.weight']) == 0
+    assert torch.all(sd['transformer.layers.0.0.4.to_gamma.bias'] == -2)
+    assert torch.all(sd['transformer.layers.0.0.3.to_v_head_gate.bias'] == 10)
+
+
+def test_sample_signature_keeps_reference_kwargs():
+    from e2_tts_pytorch.e2_tts_crossatt3 import E2TTS, Transformer, MelSpec, EncodecWrapper, DurationPredictor  # noqa: F401
+    ref_kwargs = ['text', 'lens', 'duration', 'steps', 'cfg_strength', 'remove_parallel_component', 'sway_sampling', 'max_duration',
+                  'vocoder', 'return_raw_output', 'save_to_filename', 'prompt', 'video_drop_prompt', 'audio_drop_prompt', 'video_paths',
+                  'frames', 'midis']                                                    # e2_tts_crossatt3.py:2128-2148
+    sig = inspect.signature(E2TTS.sample)
+    for k in ref_kwargs:
+        assert k in sig.parameters, k
+    assert sig.parameters['steps'].default == 32 and sig.parameters['cfg_strength'].default == 1.
+    assert sig.parameters['remove_parallel_component'].default is True and sig.parameters['max_duration'].default == 4096
+    fsig = inspect.signature(Transformer.forward)
+    assert list(fsig.parameters)[1:] == ['x', 'times', 'mask', 'text_embed', 'frames_embed', 'context', 'context_mask']
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU behaviour')
+def test_no_cpu_fallback():
+    from e2_tts_pytorch.e2_tts_crossatt3 import E2TTS, MelSpec
+    cfg = synth.TINY
+    m = E2TTS(transformer=dict(depth=2, dim=128, dim_text=128, dim_frames=64, heads=2, dim_head=64, max_seq_len=64, if_text_conv=True),
+              if_cond_proj_in=False, if_embed_text=False, if_text_encoder2=False, num_channels=64)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        m.sample(torch.zeros(1, 8, 64), text=torch.zeros(1, 8, 128), context=torch.zeros(1, 4, 128), return_raw_output=True)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        MelSpec()(torch.zeros(1, 4096))
+
+
+def test_mel_filterbank_matches_torchaudio():
+    import torchaudio
+    from e2_tts_pytorch.e2_tts_crossatt3 import MelSpec
+    ref = torchaudio.functional.melscale_fbanks(513, 0., 12000., 100, 24000, norm=None, mel_scale='htk')
+    assert torch.allclose(MelSpec.mel_filterbank(513, 0., 12000., 100, 24000), ref, atol=1e-6)

@@ -1,0 +1,268 @@
+// Flash-style attention on tcgen05 for the x-transformers `Attention` the reference instantiates with
+// softclamp_logits=True, gate_value_heads=True (e2_tts_crossatt3.py:808,813,881,914):
+//
+//     sim = 50 * tanh(q k^T * 64^-0.5 / 50) ; key-length mask ; softmax (fp32) ; out = attn v ;
+//     out *= sigmoid(head_gate)[token, head]
+//
+// One CTA per (128-query tile, head, batch item).  S = Q K^T lives in TMEM (two 128-column buffers), the softmax
+// warps read it with tcgen05.ld, write P (bf16) into shared memory in the UMMA K-major SWIZZLE_128B layout, and
+// O += P V accumulates in TMEM over all key tiles.  Because the soft-clamp bounds every logit to [-50, 50],
+// exp(sim) cannot overflow or underflow in fp32/bf16, so no running maximum and no O rescaling is needed:
+// out = (sum_j exp(sim_j) v_j) / (sum_j exp(sim_j)) is evaluated directly.  q arrives pre-scaled by 64^-0.5 and
+// RoPE-rotated, k RoPE-rotated, V transposed ([d, keys]) -- all produced by the QKV GEMM epilogue (gemm.cu) -- so
+// both MMAs take plain K-major operands.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace e2b {
+
+int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
+constexpr int ATT_THREADS = 256;
+constexpr int ATT_BQ = 128, ATT_BK = 128, ATT_D = 64;
+constexpr int ATT_SQ = 0;                       // 16 KB  Q   [128 q, 64 d]
+constexpr int ATT_SK = 16384;                   // 2 x 16 KB  K   [128 keys, 64 d]
+constexpr int ATT_SV = ATT_SK + 2 * 16384;      // 2 x 16 KB  V^T 2 x [64 d, 64 keys]
+constexpr int ATT_SP = ATT_SV + 2 * 16384;      // 2 x 32 KB  P   2 x [128 q, 64 keys]
+constexpr int ATT_BAR = ATT_SP + 2 * 32768;
+constexpr int ATT_SMEM = ATT_BAR + 256 + 1024;
+constexpr uint32_t ATT_TMEM_COLS = 512;         // S0 @0, S1 @128, O @256
+
+// tanh(x) for the soft-clamp.  |x| = |logit|/50 is small for realistic logits, so an odd polynomial on the FMA pipe
+// (abs error < 5e-6 for |x| < 0.5) replaces the MUFU op (tanh.approx.f32 is only 2^-11 accurate, which the following
+// exp would amplify 50x); larger arguments take the exact exp-based form.
+__device__ __forceinline__ float softclamp_unit(float x) {
+  const float x2 = x * x;
+  if (x2 < 0.25f) {
+    float p = fmaf(x2, 62.0f / 2835.0f, -17.0f / 315.0f);
+    p = fmaf(x2, p, 2.0f / 15.0f);
+    p = fmaf(x2, p, -1.0f / 3.0f);
+    p = fmaf(x2, p, 1.0f);
+    return x * p;
+  }
+  const float e = ex2_approx(x * 2.8853900817779268f);     // exp(2x)
+  return 1.0f - __fdividef(2.0f, 1.0f + e);
+}
+
+struct AttnArgs {
+  CUtensorMap tmQ, tmK, tmV;
+  e2b_attn_desc d;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_constant__ AttnArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_BAR);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* kv_full = bars + 1;     // [2]
+  uint64_t* kv_empty = bars + 3;    // [2]
+  uint64_t* s_full = bars + 5;      // [2]
+  uint64_t* s_empty = bars + 7;     // [2] (128 arrivals)
+  uint64_t* p_full = bars + 9;      // [2] (128 arrivals)
+  uint64_t* p_empty = bars + 11;    // [2]
+  uint64_t* o_full = bars + 13;     // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const e2b_attn_desc& d = args.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+
+  const int kvb = d.kv_batch_mod > 0 ? b % d.kv_batch_mod : b;
+  int kv_len = d.kv_lens ? (__ldg(d.kv_lens + kvb) + d.kv_lens_add) : d.kv_rows_per_batch;
+  kv_len = min(kv_len, d.kv_rows_per_batch);
+  const int nt = (kv_len + ATT_BK - 1) / ATT_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&args.tmQ);
+    tma_prefetch_desc(&args.tmK);
+    tma_prefetch_desc(&args.tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(o_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 128);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&p_empty[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 256;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    mbar_arrive_expect_tx(q_full, 16384);
+    tma_load_2d(smem + ATT_SQ, &args.tmQ, q_full, d.q_col0 + h * ATT_D, b * d.q_rows_per_batch + qt * ATT_BQ);
+    for (int j = 0; j < nt; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&kv_empty[s], ph ^ 1);
+      mbar_arrive_expect_tx(&kv_full[s], 32768);
+      tma_load_2d(smem + ATT_SK + s * 16384, &args.tmK, &kv_full[s], d.k_col0 + h * ATT_D, kvb * d.kv_rows_per_batch + j * ATT_BK);
+      const int vrow = (kvb * d.heads + h) * ATT_D;
+      tma_load_2d(smem + ATT_SV + s * 16384, &args.tmV, &kv_full[s], j * ATT_BK, vrow);
+      tma_load_2d(smem + ATT_SV + s * 16384 + 8192, &args.tmV, &kv_full[s], j * ATT_BK + 64, vrow);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, ATT_BK);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, ATT_D);
+    const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SQ));
+    auto issue_s = [&](int j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&kv_full[s], ph);
+      mbar_wait(&s_empty[s], ph ^ 1);
+      tc_fence_after();
+      const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SK + s * 16384));
+#pragma unroll
+      for (int k = 0; k < ATT_D / 16; ++k)
+        umma_bf16_ss(tmem_base + s * ATT_BK, dq + k * UMMA_K_STEP_ENC, dk + k * UMMA_K_STEP_ENC, idesc_s, k != 0 ? 1u : 0u);
+      umma_commit(&s_full[s]);
+    };
+    mbar_wait(q_full, 0);
+    if (nt > 0) issue_s(0);
+    for (int j = 0; j < nt; ++j) {
+      if (j + 1 < nt) issue_s(j + 1);
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&p_full[s], ph);
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < ATT_BK / 16; ++kk) {
+        const int atom = kk >> 2, k4 = kk & 3;
+        const uint64_t dp = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SP + s * 32768 + atom * 16384)) + k4 * UMMA_K_STEP_ENC;
+        const uint64_t dv = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SV + s * 16384 + atom * 8192)) + k4 * UMMA_K_STEP_ENC;
+        umma_bf16_ss(tmem_o, dp, dv, idesc_o, (j | kk) != 0 ? 1u : 0u);
+      }
+      umma_commit(&kv_empty[s]);
+      umma_commit(&p_empty[s]);
+    }
+    umma_commit(o_full);
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ softmax + epilogue (thread = query row)
+    const int ew = warp - 4;
+    const int r = ew * 32 + lane;                       // row inside the tile == TMEM lane
+    const int q_pos = qt * ATT_BQ + r;
+    const bool q_valid = q_pos < d.q_rows_per_batch;
+    const bool warp_valid = (qt * ATT_BQ + ew * 32) < d.q_rows_per_batch;
+    const uint32_t lane_base = uint32_t(ew * 32) << 16;
+    const float inv_clamp = 1.0f / d.softclamp;
+    const float out_scale = d.softclamp * 1.4426950408889634f;   // clamp * log2(e)
+    const uint32_t p_row_off = (r >> 3) * 1024 + (r & 7) * 128;
+    float l = 0.f;
+
+    for (int j = 0; j < nt; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const int nvalid = min(ATT_BK, kv_len - j * ATT_BK);
+      mbar_wait(&s_full[s], ph);
+      tc_fence_after();
+      mbar_wait(&p_empty[s], ph ^ 1);
+      uint8_t* sp = smem + ATT_SP + s * 32768;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+        if (warp_valid && c * 32 < nvalid) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + lane_base + s * ATT_BK + c * 32, v);
+          tmem_ld_wait();
+          float p[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = ex2_approx(softclamp_unit(__uint_as_float(v[i]) * inv_clamp) * out_scale);
+            p[i] = (c * 32 + i < nvalid) ? e : 0.f;
+            l += p[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+        }
+        // keys c*32 .. c*32+31 -> swizzle atom (c >> 1), 16-byte chunks ((c & 1) * 4 + q) ^ (r & 7)
+        uint8_t* atom = sp + (c >> 1) * 16384 + p_row_off;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
+          *reinterpret_cast<uint4*>(atom + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&s_empty[s]);
+      fence_proxy_async_smem();
+      mbar_arrive(&p_full[s]);
+    }
+
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    float scale = 0.f;
+    if (q_valid && l > 0.f) {
+      scale = 1.0f / l;
+      if (d.hgate) scale *= __ldg(d.hgate + (size_t)(b * d.q_rows_per_batch + q_pos) * d.hgate_ld + h);
+    }
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)(b * d.q_rows_per_batch + q_pos) * d.ldo + h * ATT_D;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_o + lane_base + c * 32, v);
+      tmem_ld_wait();
+      if (q_valid) {
+        uint4* o4 = reinterpret_cast<uint4*>(op + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(v[8 * i + 0]) * scale, __uint_as_float(v[8 * i + 1]) * scale);
+          u.y = pack_bf16(__uint_as_float(v[8 * i + 2]) * scale, __uint_as_float(v[8 * i + 3]) * scale);
+          u.z = pack_bf16(__uint_as_float(v[8 * i + 4]) * scale, __uint_as_float(v[8 * i + 5]) * scale);
+          u.w = pack_bf16(__uint_as_float(v[8 * i + 6]) * scale, __uint_as_float(v[8 * i + 7]) * scale);
+          o4[i] = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+}
+
+}  // namespace e2b
+
+using namespace e2b;
+
+extern "C" int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream) {
+  if (d->batch <= 0 || d->heads <= 0 || d->q_rows_per_batch <= 0) return 0;
+  if (d->kv_rows_per_batch <= 0) { e2b_set_kernel_error("attention: kv_rows_per_batch must be positive"); return -1; }
+  if ((d->ldo % 8) || (reinterpret_cast<uintptr_t>(d->out) & 15)) { e2b_set_kernel_error("attention: out must be 16-byte aligned"); return -1; }
+  AttnArgs a;
+  a.d = *d;
+  const uint64_t q_rows = (uint64_t)d->batch * d->q_rows_per_batch;
+  const int kv_batches = d->kv_batch_mod > 0 ? d->kv_batch_mod : d->batch;
+  const uint64_t k_rows = (uint64_t)kv_batches * d->kv_rows_per_batch;
+  if (make_tmap_bf16(&a.tmQ, d->q, q_rows, (uint64_t)d->q_col0 + d->heads * 64, d->ldq, ATT_BQ)) return -1;
+  if (make_tmap_bf16(&a.tmK, d->k, k_rows, (uint64_t)d->k_col0 + d->heads * 64, d->ldk, ATT_BK)) return -1;
+  if (make_tmap_bf16(&a.tmV, d->vt, (uint64_t)kv_batches * d->heads * 64, d->kv_rows_per_batch, d->vt_ld, 64)) return -1;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e != cudaSuccess) { e2b_set_kernel_error("attention smem attribute: %s", cudaGetErrorString(e)); return -1; }
+    configured = true;
+  }
+  dim3 grid((d->q_rows_per_batch + ATT_BQ - 1) / ATT_BQ, d->heads, d->batch);
+  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { e2b_set_kernel_error("attention launch: %s", cudaGetErrorString(e)); return -1; }
+  return 0;
+}

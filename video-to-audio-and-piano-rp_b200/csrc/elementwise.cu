@@ -1,0 +1,404 @@
+// HBM-bound glue kernels of the E2 transformer forward and the sampler epilogue (sm_100a).
+//   rmsnorm        x-transformers RMSNorm / AdaptiveRMSNorm  (F.normalize eps 1e-12, * sqrt(d) * scale)
+//   dwconv         DepthwiseConv (e2_tts_crossatt3.py:495-528) + the caller's residual add (:1082,1097,1122)
+//   time_mlp/gemv  time_cond_mlp (:555-564,793-797) and every AdaptiveRMSNorm.to_gamma / AdaLNZero.to_gamma (:532-551)
+//   init_stream    register-token prepend + condition drop (:975-997, 2040-2044)
+//   guided_euler   cfg combine (+APG projection :162-173, 2106-2113), K-pass mix and the Euler update
+#include <math.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace e2b {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------ rmsnorm
+constexpr int NORM_MAX_V4 = 16;   // C <= 2048
+
+template <bool OUT_F32>
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, int ldx, void* __restrict__ yv, int ldy,
+                                                      const float* __restrict__ scale, int scale_bstride, int rows_out_total,
+                                                      int rows_per_batch, int skip_rows, int C, float sqrt_c) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows_out_total) return;
+  const int rpo = rows_per_batch - skip_rows;
+  const int b = warp / rpo, i = warp % rpo;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(b * rows_per_batch + skip_rows + i) * ldx);
+  const int nv = C >> 2;
+  float4 v[NORM_MAX_V4];
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < NORM_MAX_V4; ++k) {
+    const int idx = lane + 32 * k;
+    if (idx < nv) {
+      v[k] = xr[idx];
+      ss += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+    }
+  }
+  ss = warp_sum(ss);
+  const float inv = sqrt_c / fmaxf(sqrtf(ss), 1e-12f);
+  const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * scale_bstride);
+#pragma unroll
+  for (int k = 0; k < NORM_MAX_V4; ++k) {
+    const int idx = lane + 32 * k;
+    if (idx < nv) {
+      const float4 s = __ldg(sc + idx);
+      if constexpr (OUT_F32) {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(yv) + (size_t)warp * ldy)[idx] =
+            make_float4(v[k].x * inv * s.x, v[k].y * inv * s.y, v[k].z * inv * s.z, v[k].w * inv * s.w);
+      } else {
+        uint2 o;
+        o.x = pack_bf16(v[k].x * inv * s.x, v[k].y * inv * s.y);
+        o.y = pack_bf16(v[k].z * inv * s.z, v[k].w * inv * s.w);
+        reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(yv) + (size_t)warp * ldy)[idx] = o;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dwconv
+// One thread = one channel, walking down a segment of rows with a register ring buffer (no shared memory, every
+// input element is loaded once per segment, lanes = consecutive channels so every access is a coalesced 128 B line).
+template <int KS, int PF>
+__global__ void __launch_bounds__(128) dwconv_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ wt,
+                                                     const float* __restrict__ bias, const int* __restrict__ lens, int N, int C, int seg) {
+  constexpr int HALF = KS / 2, RS = KS + PF;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * seg;
+  const int r1 = min(N, r0 + seg);
+  const int len = lens ? min(N, __ldg(lens + b)) : N;
+  const float* xb = x + (size_t)b * N * C + c;
+  float* yb = y + (size_t)b * N * C + c;
+  float w[KS];
+#pragma unroll
+  for (int i = 0; i < KS; ++i) w[i] = __ldg(wt + (size_t)i * C + c);
+  const float bs = __ldg(bias + c);
+  auto ld = [&](int rho) -> float { return (rho >= 0 && rho < len) ? xb[(size_t)rho * C] : 0.f; };
+  float ring[RS];
+#pragma unroll
+  for (int i = 0; i < RS - 1; ++i) ring[i] = ld(r0 - HALF + i);
+  ring[RS - 1] = 0.f;
+  for (int base = r0; base < r1; base += RS) {
+#pragma unroll
+    for (int u = 0; u < RS; ++u) {
+      const int r = base + u;
+      if (r < r1) {
+        ring[(u + RS - 1) % RS] = ld(r + HALF + PF);      // slot of row r-HALF-1, no longer needed
+        float acc = bs;
+#pragma unroll
+        for (int i = 0; i < KS; ++i) acc = fmaf(w[i], ring[(u + i) % RS], acc);
+        float out;
+        if (r < len) out = ring[(u + HALF) % RS] + silu(acc);
+        else out = xb[(size_t)r * C];
+        yb[(size_t)r * C] = out;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ time conditioning
+__global__ void __launch_bounds__(256) time_mlp_kernel(const float* __restrict__ times, const float* __restrict__ fw,
+                                                       const float* __restrict__ w1, const float* __restrict__ b1, int dim,
+                                                       float* __restrict__ tcond) {
+  extern __shared__ float emb[];   // dim + 1
+  const int s = blockIdx.x;
+  const float t = times[s];
+  const int half = dim / 2;
+  for (int i = threadIdx.x; i <= dim; i += blockDim.x) {
+    float v;
+    if (i == 0) v = t;
+    else {
+      const int j = (i - 1) % half;
+      float f = t * fw[j];
+      f = f * 2.0f;
+      f = f * 3.14159265358979323846f;
+      v = (i - 1 < half) ? sinf(f) : cosf(f);
+    }
+    emb[i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < dim; j += nw) {
+    const float* wr = w1 + (size_t)j * (dim + 1);
+    float acc = 0.f;
+    for (int k = lane; k <= dim; k += 32) acc = fmaf(wr[k], emb[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) tcond[(size_t)s * dim + j] = silu(acc + b1[j]);
+  }
+}
+
+constexpr int GEMV_MAX_K = 64;    // dim <= 2048
+__global__ void __launch_bounds__(256) time_gemv_kernel(const float* __restrict__ tcond, int nt, int dim, const float* const* __restrict__ w,
+                                                        const float* const* __restrict__ bvec, const int* __restrict__ act, int nmat,
+                                                        float* __restrict__ out) {
+  const int m = blockIdx.y;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= dim) return;
+  const float* wr = w[m] + (size_t)j * dim;
+  float wreg[GEMV_MAX_K];
+  const int nk = (dim + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < GEMV_MAX_K; ++k)
+    if (k < nk) wreg[k] = (lane + 32 * k < dim) ? __ldg(wr + lane + 32 * k) : 0.f;
+  const float bj = bvec[m] ? bvec[m][j] : 0.f;
+  const int a = act[m];
+  for (int s = 0; s < nt; ++s) {
+    const float* tc = tcond + (size_t)s * dim;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < GEMV_MAX_K; ++k)
+      if (k < nk) acc = fmaf(wreg[k], (lane + 32 * k < dim) ? __ldg(tc + lane + 32 * k) : 0.f, acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float v = acc + bj;
+      out[((size_t)s * nmat + m) * dim + j] = (a == 0) ? v + 1.0f : 1.0f / (1.0f + expf(-v));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ stream init
+__global__ void __launch_bounds__(256) init_stream_kernel(float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_b16,
+                                                          const float* __restrict__ regs, const float* __restrict__ src, int src_batches,
+                                                          const unsigned char* __restrict__ drop, const float* __restrict__ add_table,
+                                                          int batch, int n, int R, int C, int regs_only) {
+  const int nv = C >> 2;
+  const int rows = regs_only ? R : (R + n);
+  const size_t total = (size_t)batch * rows * nv;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int v = idx % nv;
+    const size_t rr = idx / nv;
+    const int pos = rr % rows, b = rr / rows;
+    float4 val;
+    if (pos < R) val = __ldg(reinterpret_cast<const float4*>(regs + (size_t)pos * C) + v);
+    else {
+      if (src && !(drop && drop[b])) val = __ldg(reinterpret_cast<const float4*>(src + ((size_t)(b % src_batches) * n + (pos - R)) * C) + v);
+      else val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (add_table) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(add_table + (size_t)(pos - R) * C) + v);
+        val.x += a.x; val.y += a.y; val.z += a.z; val.w += a.w;
+      }
+    }
+    const size_t o = ((size_t)b * (R + n) + pos) * C;
+    reinterpret_cast<float4*>(dst + o)[v] = val;
+    if (dst_b16) {
+      uint2 u;
+      u.x = pack_bf16(val.x, val.y);
+      u.y = pack_bf16(val.z, val.w);
+      reinterpret_cast<uint2*>(dst_b16 + o)[v] = u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_pad_kernel(const float* __restrict__ src, int lds, __nv_bfloat16* __restrict__ dst, int ldd,
+                                                       size_t rows, int C) {
+  const size_t total = rows * ldd;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = idx % ldd;
+    const size_t r = idx / ldd;
+    dst[idx] = __float2bfloat16_rn(c < C ? src[r * lds + c] : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ guided Euler
+constexpr int EULER_MAX_P = 8;
+struct EulerW { float w[EULER_MAX_P]; };
+
+// scratch[2*b] += <p0 - p1, p0>, scratch[2*b+1] += <p0, p0>  in fp64 (reference `project` runs in double)
+__global__ void __launch_bounds__(256) apg_reduce_kernel(const float* __restrict__ pred, size_t pass_stride, size_t per_sample,
+                                                         double* __restrict__ scratch) {
+  const int b = blockIdx.y;
+  const float4* p0 = reinterpret_cast<const float4*>(pred + (size_t)b * per_sample);
+  const float4* p1 = reinterpret_cast<const float4*>(pred + pass_stride + (size_t)b * per_sample);
+  double a = 0.0, c = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_sample / 4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 u = p0[i], v = p1[i];
+    a += (double)(u.x - v.x) * u.x + (double)(u.y - v.y) * u.y + (double)(u.z - v.z) * u.z + (double)(u.w - v.w) * u.w;
+    c += (double)u.x * u.x + (double)u.y * u.y + (double)u.z * u.z + (double)u.w * u.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  __shared__ double sa[8], sc[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sa[warp] = a; sc[warp] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0, tc = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { ta += sa[i]; tc += sc[i]; }
+    atomicAdd(scratch + 2 * b, ta);
+    atomicAdd(scratch + 2 * b + 1, tc);
+  }
+}
+
+__global__ void __launch_bounds__(256) guided_euler_kernel(float* __restrict__ y, const float* __restrict__ pred, int P, size_t pass_stride,
+                                                           size_t per_sample, size_t total4, EulerW gw, float dt, int apg,
+                                                           float keep_parallel, const double* __restrict__ scratch,
+                                                           __nv_bfloat16* __restrict__ yb, int n_copies) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 p0 = reinterpret_cast<const float4*>(pred)[i];
+    float v[4] = {p0.x, p0.y, p0.z, p0.w};
+    const float q0[4] = {p0.x, p0.y, p0.z, p0.w};
+    if (apg) {
+      // upd = p0 - p1 ; par = (<upd,p0>/max(|p0|,1e-12)^2) p0 ; upd' = (upd - par) + par*keep   (fp64 like the reference)
+      const int b = (int)((i * 4) / per_sample);
+      const double a = scratch[2 * b];
+      const double nrm = fmax(sqrt(scratch[2 * b + 1]), 1e-12);
+      const double coef = a / (nrm * nrm);
+      const float4 p1 = reinterpret_cast<const float4*>(pred + pass_stride)[i];
+      const float q1[4] = {p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double upd = (double)(q0[e] - q1[e]);
+        const double par = coef * (double)q0[e];
+        const float orth = (float)(upd - par);
+        const float upd2 = orth + (float)par * keep_parallel;
+        v[e] = q0[e] + upd2 * gw.w[0];
+      }
+    } else {
+      for (int k = 1; k < P; ++k) {
+        const float4 pk = reinterpret_cast<const float4*>(pred + (size_t)k * pass_stride)[i];
+        const float wk = gw.w[k - 1];
+        v[0] += (q0[0] - pk.x) * wk;
+        v[1] += (q0[1] - pk.y) * wk;
+        v[2] += (q0[2] - pk.z) * wk;
+        v[3] += (q0[3] - pk.w) * wk;
+      }
+    }
+    float4 yy = reinterpret_cast<float4*>(y)[i];
+    yy.x += dt * v[0]; yy.y += dt * v[1]; yy.z += dt * v[2]; yy.w += dt * v[3];
+    reinterpret_cast<float4*>(y)[i] = yy;
+    if (yb) {
+      uint2 u;
+      u.x = pack_bf16(yy.x, yy.y);
+      u.y = pack_bf16(yy.z, yy.w);
+      for (int cpy = 0; cpy < n_copies; ++cpy) reinterpret_cast<uint2*>(yb + (size_t)cpy * total4 * 4)[i] = u;
+    }
+  }
+}
+
+static int grid_for(size_t work_items, int block, int max_blocks = 148 * 16) {
+  size_t g = (work_items + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > (size_t)max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { e2b_set_kernel_error("%s launch: %s", what, cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+
+}  // namespace e2b
+
+using namespace e2b;
+
+extern "C" int e2b_rmsnorm_launch(const float* x, int ldx, void* y, int ldy, const float* scale, int scale_bstride, int batch,
+                                  int rows_per_batch, int skip_rows, int C, int out_f32, cudaStream_t stream) {
+  if (C % 4 || C > NORM_MAX_V4 * 128 || ldx % 4 || ldy % 4) { e2b_set_kernel_error("rmsnorm: C=%d unsupported", C); return -1; }
+  const int rows_out = batch * (rows_per_batch - skip_rows);
+  if (rows_out <= 0) return 0;
+  const int blocks = (rows_out + 7) / 8;
+  if (out_f32)
+    rmsnorm_kernel<true><<<blocks, 256, 0, stream>>>(x, ldx, y, ldy, scale, scale_bstride, rows_out, rows_per_batch, skip_rows, C,
+                                                     sqrtf((float)C));
+  else
+    rmsnorm_kernel<false><<<blocks, 256, 0, stream>>>(x, ldx, y, ldy, scale, scale_bstride, rows_out, rows_per_batch, skip_rows, C,
+                                                      sqrtf((float)C));
+  return check_launch("rmsnorm");
+}
+
+extern "C" int e2b_dwconv_launch(const float* x, float* y, const float* w, const float* bias, const int* lens, int batch, int N,
+                                 int C, int ksize, cudaStream_t stream) {
+  if (ksize != 31) { e2b_set_kernel_error("dwconv: kernel size %d unsupported (31 only)", ksize); return -1; }
+  if (batch <= 0 || N <= 0) return 0;
+  const int nseg = (N + 95) / 96;
+  const int seg = (N + nseg - 1) / nseg;
+  dim3 grid((C + 127) / 128, nseg, batch);
+  dwconv_kernel<31, 9><<<grid, 128, 0, stream>>>(x, y, w, bias, lens, N, C, seg);
+  return check_launch("dwconv");
+}
+
+extern "C" int e2b_time_mlp_launch(const float* times, int nt, const float* fourier_w, const float* w1, const float* b1, int dim,
+                                   float* tcond, cudaStream_t stream) {
+  if (nt <= 0) return 0;
+  time_mlp_kernel<<<nt, 256, (dim + 1) * sizeof(float), stream>>>(times, fourier_w, w1, b1, dim, tcond);
+  return check_launch("time_mlp");
+}
+
+extern "C" int e2b_time_gemv_launch(const float* tcond, int nt, int dim, const float* const* w, const float* const* b, const int* act,
+                                    int nmat, float* out, cudaStream_t stream) {
+  if (nt <= 0 || nmat <= 0) return 0;
+  if (dim > GEMV_MAX_K * 32) { e2b_set_kernel_error("time_gemv: dim %d too large", dim); return -1; }
+  dim3 grid((dim + 7) / 8, nmat);
+  time_gemv_kernel<<<grid, 256, 0, stream>>>(tcond, nt, dim, w, b, act, nmat, out);
+  return check_launch("time_gemv");
+}
+
+extern "C" int e2b_init_stream_launch(float* dst, void* dst_b16, const float* registers, const float* src, int src_batches,
+                                      const unsigned char* drop, const float* add_table, int batch, int n, int R, int C,
+                                      cudaStream_t stream) {
+  if (C % 4) { e2b_set_kernel_error("init_stream: C %% 4 != 0"); return -1; }
+  const int regs_only = (src_batches < 0);
+  const size_t total = (size_t)batch * (regs_only ? R : R + n) * (C / 4);
+  if (!total) return 0;
+  init_stream_kernel<<<grid_for(total, 256), 256, 0, stream>>>(dst, reinterpret_cast<__nv_bfloat16*>(dst_b16), registers, src,
+                                                               src_batches > 0 ? src_batches : 1, drop, add_table, batch, n, R, C,
+                                                               regs_only);
+  return check_launch("init_stream");
+}
+
+namespace e2b {
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  const size_t total = (size_t)rows * cols;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = i % cols, r = i / cols;
+    dst[(size_t)c * rows + r] = src[i];
+  }
+}
+}  // namespace e2b
+
+extern "C" int e2b_transpose_launch(const float* src, float* dst, int rows, int cols, cudaStream_t stream) {
+  const size_t total = (size_t)rows * cols;
+  if (!total) return 0;
+  e2b::transpose_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, dst, rows, cols);
+  return check_launch("transpose");
+}
+
+extern "C" int e2b_cast_pad_launch(const float* src, int lds, void* dst, int ldd, int rows, int C, cudaStream_t stream) {
+  const size_t total = (size_t)rows * ldd;
+  if (!total) return 0;
+  cast_pad_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, (size_t)rows, C);
+  return check_launch("cast_pad");
+}
+
+extern "C" int e2b_guided_euler_launch(float* y, const float* pred, int P, int B, long long per_sample, const float* w, float dt,
+                                       int apg, float keep_parallel, double* scratch, void* y_b16, int n_copies, cudaStream_t stream) {
+  if (P < 1 || P > EULER_MAX_P) { e2b_set_kernel_error("guided_euler: P=%d out of range", P); return -1; }
+  if (per_sample % 4) { e2b_set_kernel_error("guided_euler: per-sample size must be a multiple of 4"); return -1; }
+  if (apg && (P != 2 || !scratch)) { e2b_set_kernel_error("guided_euler: APG needs exactly one guidance pass and scratch"); return -1; }
+  const size_t pass_stride = (size_t)B * per_sample;
+  EulerW gw;
+  for (int k = 0; k < EULER_MAX_P; ++k) gw.w[k] = (k < P - 1) ? w[k] : 0.f;
+  if (apg) {
+    cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * B, stream);
+    dim3 g(grid_for(per_sample / 4, 256, 64), B);
+    apg_reduce_kernel<<<g, 256, 0, stream>>>(pred, pass_stride, per_sample, scratch);
+    if (check_launch("apg_reduce")) return -1;
+  }
+  const size_t total4 = pass_stride / 4;
+  guided_euler_kernel<<<grid_for(total4, 256), 256, 0, stream>>>(y, pred, P, pass_stride, per_sample, total4, gw, dt, apg,
+                                                                keep_parallel, scratch, reinterpret_cast<__nv_bfloat16*>(y_b16), n_copies);
+  return check_launch("guided_euler");
+}

@@ -1,0 +1,795 @@
+// libe2b engine: weight repacking, workspace, the 3-stream E2 transformer forward as a sequence of sm_100a kernels,
+// and the CFM sampler loop.  Host-side C++ only (no torch); see include/e2b.h for the C-ABI and the reference
+// lines each entry replaces.  Layer dataflow follows Transformer.forward, e2_tts_crossatt3.py:941-1143:
+//   text -> frames -> cross-condition -> U-Net skip -> conv -> self-attn -> cross-attn(T5) -> GEGLU FF.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/e2b.h"
+#include "kernels.h"
+
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+thread_local char g_api_err[768] = "";
+
+struct Stream3 {   // per-stream (text / frames) layer weights
+  float *conv_w = nullptr, *conv_b = nullptr, *g1 = nullptr, *g2 = nullptr, *hg_b = nullptr, *ff1_b = nullptr, *ff2_b = nullptr;
+  bf16 *qkv_w = nullptr, *out_w = nullptr, *ff1_w = nullptr, *ff2_w = nullptr;
+};
+struct LayerW {
+  bf16 *skip_w = nullptr, *qkv_w = nullptr, *out_w = nullptr, *q2_w = nullptr, *kv2_w = nullptr, *out2_w = nullptr, *ff1_w = nullptr,
+       *ff2_w = nullptr;
+  float *conv_w = nullptr, *conv_b = nullptr, *hg_b = nullptr, *hg2_b = nullptr, *ff1_b = nullptr, *ff2_b = nullptr;
+  Stream3 t, f;
+  bf16 *tfa_w = nullptr, *at_w = nullptr, *af_w = nullptr;
+};
+
+}  // namespace
+
+struct e2b_handle {
+  e2b_config cfg{};
+  int HD = 0, HDt = 0, HDf = 0, inner = 0, inner_t = 0, inner_f = 0, nmat = 0;
+  bool weights_loaded = false;
+  std::vector<void*> wallocs, sallocs;
+  std::string err;
+  long long launches = 0;
+
+  // global weights
+  float *registers = nullptr, *t_registers = nullptr, *f_registers = nullptr, *abs_pos = nullptr, *final_g = nullptr;
+  float *fourier_w = nullptr, *time_w1 = nullptr, *time_b1 = nullptr;
+  float *proj_in_b = nullptr, *to_pred_b = nullptr, *pf_b = nullptr;
+  bf16 *proj_in_w = nullptr, *to_pred_w = nullptr, *pf_w = nullptr;
+  float* rope = nullptr;            // [max_pos, 32, 2]
+  int rope_rows = 0;
+  std::vector<LayerW> L;
+  const float** tm_w = nullptr;     // device arrays for the time GEMVs
+  const float** tm_b = nullptr;
+  int* tm_act = nullptr;
+
+  // prepared shape
+  int B = 0, n = 0, nc = 0, P = 0, Pctx = 0, N = 0, Bt = 0, Npad = 0, ncpad = 0;
+  size_t M = 0;
+  bool conditions_set = false;
+  float *x[2] = {nullptr, nullptr}, *text[2] = {nullptr, nullptr}, *frames[2] = {nullptr, nullptr};
+  bf16 *xb = nullptr, *textb = nullptr, *framesb = nullptr, *xtmpb = nullptr, *nb = nullptr, *qk = nullptr, *vt = nullptr, *ob = nullptr,
+       *hb = nullptr, *ybf = nullptr, *finalb = nullptr, *fin = nullptr, *ctxb = nullptr;
+  std::vector<bf16*> skipb, k2, vt2;
+  float *hg = nullptr, *fr0 = nullptr, *clip = nullptr, *pred = nullptr, *gam = nullptr, *tcond = nullptr, *times_dev = nullptr;
+  double* apg_scratch = nullptr;
+  int *lens_dev = nullptr, *ctx_lens_dev = nullptr;
+  unsigned char* drop_clip_dev = nullptr;
+  int gam_capacity = 0;
+  int pass_flags[8] = {0};
+};
+
+namespace {
+
+int fail(e2b_handle* h, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_api_err, sizeof(g_api_err), fmt, ap);
+  va_end(ap);
+  if (h) h->err = g_api_err;
+  return -1;
+}
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    if ((call) != 0) return fail(h, "%s failed: %s", #call, e2b_kernel_last_error());             \
+    ++h->launches;                                                                                \
+  } while (0)
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) return fail(h, "%s: %s", #call, cudaGetErrorString(e__));            \
+  } while (0)
+
+template <typename T>
+int dalloc(e2b_handle* h, std::vector<void*>& pool, T** p, size_t count) {
+  void* q = nullptr;
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = sizeof(T);
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) return fail(h, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+  e = cudaMemset(q, 0, bytes);
+  if (e != cudaSuccess) return fail(h, "cudaMemset: %s", cudaGetErrorString(e));
+  pool.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return 0;
+}
+#define DA(pool, ptr, count)                             \
+  do {                                                   \
+    if (dalloc(h, pool, &(ptr), (size_t)(count))) return -1; \
+  } while (0)
+
+void free_pool(std::vector<void*>& pool) {
+  for (void* p : pool) cudaFree(p);
+  pool.clear();
+}
+
+inline int rup(int v, int m) { return (v + m - 1) / m * m; }
+
+struct WMap {
+  std::map<std::string, const e2b_tensor*> m;
+  const e2b_tensor* get(const std::string& k) const {
+    auto it = m.find(k);
+    return it == m.end() ? nullptr : it->second;
+  }
+};
+
+// ------------------------------------------------------------------------------------------ weight packing helpers
+int need(e2b_handle* h, const WMap& w, const std::string& name, const e2b_tensor** out, long long s0, long long s1 = -1, long long s2 = -1) {
+  const e2b_tensor* t = w.get(name);
+  if (!t) return fail(h, "load_weights: missing tensor '%s'", name.c_str());
+  long long want[3] = {s0, s1, s2};
+  int nd = s1 < 0 ? 1 : (s2 < 0 ? 2 : 3);
+  if (t->ndim != nd) return fail(h, "load_weights: '%s' has ndim %d, expected %d", name.c_str(), t->ndim, nd);
+  for (int i = 0; i < nd; ++i)
+    if (t->shape[i] != want[i])
+      return fail(h, "load_weights: '%s' dim %d is %lld, expected %lld", name.c_str(), i, t->shape[i], want[i]);
+  *out = t;
+  return 0;
+}
+
+int copy_f32(e2b_handle* h, const WMap& w, const std::string& name, float** dst, long long s0, long long s1, cudaStream_t st) {
+  const e2b_tensor* t;
+  if (need(h, w, name, &t, s0, s1)) return -1;
+  const size_t cnt = (size_t)s0 * (s1 < 0 ? 1 : s1);
+  DA(h->wallocs, *dst, cnt);
+  CU(cudaMemcpyAsync(*dst, t->dev, cnt * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// dst rows [row0, row0+rows) of a bf16 [*, ldd] matrix <- src fp32 rows [srow0, ...) of [*, K]
+int cast_rows(e2b_handle* h, const float* src, int K, int srow0, bf16* dst, int ldd, int row0, int rows, cudaStream_t st) {
+  CK(e2b_cast_pad_launch(src + (size_t)srow0 * K, K, dst + (size_t)row0 * ldd, ldd, rows, K, st));
+  return 0;
+}
+
+int pack_linear(e2b_handle* h, const WMap& w, const std::string& name, bf16** dst, int out_f, int in_f, cudaStream_t st, int ldd = 0) {
+  const e2b_tensor* t;
+  if (need(h, w, name, &t, out_f, in_f)) return -1;
+  if (!ldd) ldd = in_f;
+  DA(h->wallocs, *dst, (size_t)out_f * ldd);
+  return cast_rows(h, t->dev, in_f, 0, *dst, ldd, 0, out_f, st);
+}
+
+// [Wq; Wk; Wv; Wgate] (or a subset) -> one bf16 matrix
+int pack_concat(e2b_handle* h, const WMap& w, const std::vector<std::pair<std::string, int>>& parts, int in_f, bf16** dst, cudaStream_t st) {
+  int rows = 0;
+  for (auto& p : parts) rows += p.second;
+  DA(h->wallocs, *dst, (size_t)rows * in_f);
+  int r = 0;
+  for (auto& p : parts) {
+    const e2b_tensor* t;
+    if (need(h, w, p.first, &t, p.second, in_f)) return -1;
+    if (cast_rows(h, t->dev, in_f, 0, *dst, in_f, r, p.second, st)) return -1;
+    r += p.second;
+  }
+  return 0;
+}
+
+// GEGLU interleave: packed tile of 256 rows = 128 value rows then the matching 128 gate rows.
+int pack_geglu(e2b_handle* h, const WMap& w, const std::string& base, int dim, int inner, bf16** wd, float** bd, cudaStream_t st) {
+  const e2b_tensor *tw, *tb;
+  if (need(h, w, base + ".weight", &tw, 2 * inner, dim) || need(h, w, base + ".bias", &tb, 2 * inner)) return -1;
+  if (inner % 128) return fail(h, "GEGLU inner dim %d must be a multiple of 128", inner);
+  DA(h->wallocs, *wd, (size_t)2 * inner * dim);
+  DA(h->wallocs, *bd, (size_t)2 * inner);
+  for (int t = 0; t < inner / 128; ++t) {
+    if (cast_rows(h, tw->dev, dim, t * 128, *wd, dim, t * 256, 128, st)) return -1;
+    if (cast_rows(h, tw->dev, dim, inner + t * 128, *wd, dim, t * 256 + 128, 128, st)) return -1;
+    CU(cudaMemcpyAsync(*bd + t * 256, tb->dev + t * 128, 128 * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(*bd + t * 256 + 128, tb->dev + inner + t * 128, 128 * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+int pack_conv(e2b_handle* h, const WMap& w, const std::string& base, int C, float** wd, float** bd, cudaStream_t st) {
+  const e2b_tensor* tw;
+  const int ks = h->cfg.kernel_size;
+  if (need(h, w, base + ".dw_conv1d.0.weight", &tw, C, 1, ks)) return -1;
+  DA(h->wallocs, *wd, (size_t)ks * C);
+  CK(e2b_transpose_launch(tw->dev, *wd, C, ks, st));
+  return copy_f32(h, w, base + ".dw_conv1d.0.bias", bd, C, -1, st);
+}
+
+int pack_stream(e2b_handle* h, const WMap& w, const std::string& p, int C, int heads, int inner, Stream3& s, cudaStream_t st) {
+  const int HDs = heads * 64;
+  if (pack_conv(h, w, p + "0", C, &s.conv_w, &s.conv_b, st)) return -1;
+  if (copy_f32(h, w, p + "1.g", &s.g1, C, -1, st)) return -1;
+  if (pack_concat(h, w, {{p + "2.to_q.weight", HDs}, {p + "2.to_k.weight", HDs}, {p + "2.to_v.weight", HDs}, {p + "2.to_v_head_gate.weight", heads}},
+                  C, &s.qkv_w, st)) return -1;
+  if (copy_f32(h, w, p + "2.to_v_head_gate.bias", &s.hg_b, heads, -1, st)) return -1;
+  if (pack_linear(h, w, p + "2.to_out.weight", &s.out_w, C, HDs, st)) return -1;
+  if (copy_f32(h, w, p + "3.g", &s.g2, C, -1, st)) return -1;
+  if (pack_geglu(h, w, p + "4.ff.0.proj", C, inner, &s.ff1_w, &s.ff1_b, st)) return -1;
+  if (pack_linear(h, w, p + "4.ff.2.weight", &s.ff2_w, C, inner, st)) return -1;
+  return copy_f32(h, w, p + "4.ff.2.bias", &s.ff2_b, C, -1, st);
+}
+
+void free_workspace(e2b_handle* h) {
+  free_pool(h->sallocs);
+  h->skipb.clear();
+  h->k2.clear();
+  h->vt2.clear();
+  h->B = h->n = h->nc = h->P = 0;
+  h->gam_capacity = 0;
+  h->conditions_set = false;
+}
+
+// ------------------------------------------------------------------------------------------ gemm descriptor helpers
+e2b_gemm_desc gd(size_t M, int N, int K, const void* a, int lda, const void* w) {
+  e2b_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.M = (int)M; d.N = N; d.K = K;
+  d.num_src = 1; d.a[0] = a; d.lda[0] = lda; d.ka[0] = K;
+  d.w = w; d.ldw = K;
+  return d;
+}
+
+struct GamRef { const float* p; int bstride; };
+
+// time tables: gam[s, m, :] for nt times given on the host
+int compute_time_tables(e2b_handle* h, const float* times_host, int nt, cudaStream_t st) {
+  const int dim = h->cfg.dim;
+  if (nt > h->gam_capacity) return fail(h, "time tables: %d times exceed capacity %d", nt, h->gam_capacity);
+  CU(cudaMemcpyAsync(h->times_dev, times_host, nt * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(e2b_time_mlp_launch(h->times_dev, nt, h->fourier_w, h->time_w1, h->time_b1, dim, h->tcond, st));
+  CK(e2b_time_gemv_launch(h->tcond, nt, dim, h->tm_w, h->tm_b, h->tm_act, h->nmat, h->gam, st));
+  return 0;
+}
+
+int self_attention(e2b_handle* h, int C, int heads, const bf16* w_qkv, const float* hg_b, const bf16* nb, cudaStream_t st) {
+  const int HDs = heads * 64;
+  e2b_gemm_desc d = gd(h->M, 3 * HDs + heads, C, nb, C, w_qkv);
+  d.epi = E2B_EPI_QKV;
+  d.out = h->qk; d.ldo = 2 * HDs;
+  d.q_end = HDs; d.k_end = 2 * HDs; d.v_end = 3 * HDs;
+  d.q_scale = 0.125f;
+  d.rope = h->rope; d.pos_off = 0; d.rows_per_batch = h->N;
+  d.vt = h->vt; d.vt_ld = h->Npad; d.heads_v = heads;
+  d.hgate = h->hg; d.hgate_ld = heads; d.hgate_bias = hg_b;
+  CK(e2b_gemm_launch(&d, st));
+  e2b_attn_desc a;
+  memset(&a, 0, sizeof(a));
+  a.batch = h->Bt; a.heads = heads; a.q_rows_per_batch = h->N; a.kv_rows_per_batch = h->N;
+  a.q = h->qk; a.ldq = 2 * HDs; a.q_col0 = 0;
+  a.k = h->qk; a.ldk = 2 * HDs; a.k_col0 = HDs;
+  a.vt = h->vt; a.vt_ld = h->Npad;
+  a.kv_lens = h->lens_dev; a.kv_lens_add = 0;
+  a.hgate = h->hg; a.hgate_ld = heads;
+  a.out = h->ob; a.ldo = HDs;
+  a.softclamp = 50.0f;
+  CK(e2b_attention_launch(&a, st));
+  return 0;
+}
+
+int side_stream(e2b_handle* h, float* (&s)[2], bf16* sb, int C, int heads, int inner, const Stream3& w, cudaStream_t st) {
+  const int HDs = heads * 64;
+  CK(e2b_dwconv_launch(s[0], s[1], w.conv_w, w.conv_b, h->lens_dev, h->Bt, h->N, C, h->cfg.kernel_size, st));
+  std::swap(s[0], s[1]);
+  CK(e2b_rmsnorm_launch(s[0], C, h->nb, C, w.g1, 0, h->Bt, h->N, 0, C, 0, st));
+  if (self_attention(h, C, heads, w.qkv_w, w.hg_b, h->nb, st)) return -1;
+  {
+    e2b_gemm_desc d = gd(h->M, C, HDs, h->ob, HDs, w.out_w);
+    d.epi = E2B_EPI_RESID;
+    d.out = s[0]; d.ldo = C; d.resid = s[0]; d.ldr = C;
+    d.lens = h->lens_dev; d.rows_per_batch = h->N;
+    CK(e2b_gemm_launch(&d, st));
+  }
+  CK(e2b_rmsnorm_launch(s[0], C, h->nb, C, w.g2, 0, h->Bt, h->N, 0, C, 0, st));
+  {
+    e2b_gemm_desc d = gd(h->M, 2 * inner, C, h->nb, C, w.ff1_w);
+    d.epi = E2B_EPI_GEGLU; d.bias = w.ff1_b; d.out = h->hb; d.ldo = inner;
+    CK(e2b_gemm_launch(&d, st));
+  }
+  {
+    e2b_gemm_desc d = gd(h->M, C, inner, h->hb, inner, w.ff2_w);
+    d.epi = E2B_EPI_RESID; d.bias = w.ff2_b;
+    d.out = s[0]; d.ldo = C; d.resid = s[0]; d.ldr = C;
+    d.out_b16 = sb; d.ldo_b16 = C;
+    CK(e2b_gemm_launch(&d, st));
+  }
+  return 0;
+}
+
+// Streams x/text/frames (fp32) and xb (bf16 of x) are initialised; gam = time tables for this call.
+int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
+  const e2b_config& c = h->cfg;
+  const int dim = c.dim, dt = c.dim_text, df = c.dim_frames, H = c.heads;
+  const int HD = h->HD;
+  const size_t M = h->M;
+  const size_t Mc = (size_t)h->Pctx * h->B * h->N;
+  auto G = [&](int layer, int which) { return gam.p + (size_t)(layer * 6 + which) * dim; };
+
+  for (int l = 0; l < c.depth; ++l) {
+    const LayerW& w = h->L[l];
+    if (side_stream(h, h->text, h->textb, dt, H, h->inner_t, w.t, st)) return -1;
+    if (side_stream(h, h->frames, h->framesb, df, c.frames_heads, h->inner_f, w.f, st)) return -1;
+
+    // cross condition (all three read the pre-update bf16 copies)
+    bf16* xnew_b = (l < c.depth / 2) ? h->skipb[l] : h->xtmpb;
+    {
+      e2b_gemm_desc d = gd(M, dim, dim + dt + df, h->xb, dim, w.tfa_w);
+      d.num_src = 3;
+      d.ka[0] = dim;
+      d.a[1] = h->textb; d.lda[1] = dt; d.ka[1] = dt;
+      d.a[2] = h->framesb; d.lda[2] = df; d.ka[2] = df;
+      d.epi = E2B_EPI_RESID;
+      d.out = h->x[0]; d.ldo = dim; d.resid = h->x[0]; d.ldr = dim;
+      d.out_b16 = xnew_b; d.ldo_b16 = dim;
+      CK(e2b_gemm_launch(&d, st));
+    }
+    if (w.at_w) {
+      e2b_gemm_desc d = gd(M, dt, dim + dt, h->xb, dim, w.at_w);
+      d.num_src = 2; d.ka[0] = dim;
+      d.a[1] = h->textb; d.lda[1] = dt; d.ka[1] = dt;
+      d.epi = E2B_EPI_RESID;
+      d.out = h->text[0]; d.ldo = dt; d.resid = h->text[0]; d.ldr = dt;
+      CK(e2b_gemm_launch(&d, st));
+      e2b_gemm_desc e = gd(M, df, dim + df, h->xb, dim, w.af_w);
+      e.num_src = 2; e.ka[0] = dim;
+      e.a[1] = h->framesb; e.lda[1] = df; e.ka[1] = df;
+      e.epi = E2B_EPI_RESID;
+      e.out = h->frames[0]; e.ldo = df; e.resid = h->frames[0]; e.ldr = df;
+      CK(e2b_gemm_launch(&e, st));
+    }
+    // U-Net skip
+    if (l >= c.depth / 2) {
+      e2b_gemm_desc d = gd(M, dim, 2 * dim, h->xtmpb, dim, w.skip_w);
+      d.num_src = 2; d.ka[0] = dim;
+      d.a[1] = h->skipb[c.depth - 1 - l]; d.lda[1] = dim; d.ka[1] = dim;
+      d.epi = E2B_EPI_F32;
+      d.out = h->x[0]; d.ldo = dim;
+      CK(e2b_gemm_launch(&d, st));
+    }
+    // audio stream
+    CK(e2b_dwconv_launch(h->x[0], h->x[1], w.conv_w, w.conv_b, h->lens_dev, h->Bt, h->N, dim, c.kernel_size, st));
+    std::swap(h->x[0], h->x[1]);
+    CK(e2b_rmsnorm_launch(h->x[0], dim, h->nb, dim, G(l, 0), gam.bstride, h->Bt, h->N, 0, dim, 0, st));
+    if (self_attention(h, dim, H, w.qkv_w, w.hg_b, h->nb, st)) return -1;
+    {
+      e2b_gemm_desc d = gd(M, dim, HD, h->ob, HD, w.out_w);
+      d.epi = E2B_EPI_RESID;
+      d.out = h->x[0]; d.ldo = dim; d.resid = h->x[0]; d.ldr = dim;
+      d.gate = G(l, 1); d.gate_bstride = gam.bstride;
+      d.lens = h->lens_dev; d.rows_per_batch = h->N;
+      CK(e2b_gemm_launch(&d, st));
+    }
+    // cross attention to the T5 context: only for passes whose context is live (a zero context gives exactly 0)
+    if (Mc > 0) {
+      CK(e2b_rmsnorm_launch(h->x[0], dim, h->nb, dim, G(l, 2), gam.bstride, h->Pctx * h->B, h->N, 0, dim, 0, st));
+      e2b_gemm_desc d = gd(Mc, HD + H, dim, h->nb, dim, w.q2_w);
+      d.epi = E2B_EPI_QKV;
+      d.out = h->qk; d.ldo = HD;
+      d.q_end = HD; d.k_end = HD; d.v_end = HD;
+      d.q_scale = 0.125f;
+      d.rope = h->rope; d.pos_off = 0; d.rows_per_batch = h->N;
+      d.hgate = h->hg; d.hgate_ld = H; d.hgate_bias = w.hg2_b;
+      CK(e2b_gemm_launch(&d, st));
+      e2b_attn_desc a;
+      memset(&a, 0, sizeof(a));
+      a.batch = h->Pctx * h->B; a.heads = H; a.q_rows_per_batch = h->N; a.kv_rows_per_batch = h->nc;
+      a.q = h->qk; a.ldq = HD; a.q_col0 = 0;
+      a.k = h->k2[l]; a.ldk = HD; a.k_col0 = 0;
+      a.vt = h->vt2[l]; a.vt_ld = h->ncpad;
+      a.kv_batch_mod = h->B;
+      a.kv_lens = h->ctx_lens_dev; a.kv_lens_add = 0;
+      a.hgate = h->hg; a.hgate_ld = H;
+      a.out = h->ob; a.ldo = HD;
+      a.softclamp = 50.0f;
+      CK(e2b_attention_launch(&a, st));
+      e2b_gemm_desc o = gd(Mc, dim, HD, h->ob, HD, w.out2_w);
+      o.epi = E2B_EPI_RESID;
+      o.out = h->x[0]; o.ldo = dim; o.resid = h->x[0]; o.ldr = dim;
+      o.gate = G(l, 3); o.gate_bstride = gam.bstride;
+      o.lens = h->lens_dev; o.rows_per_batch = h->N;
+      CK(e2b_gemm_launch(&o, st));
+    }
+    CK(e2b_rmsnorm_launch(h->x[0], dim, h->nb, dim, G(l, 4), gam.bstride, h->Bt, h->N, 0, dim, 0, st));
+    {
+      e2b_gemm_desc d = gd(M, 2 * h->inner, dim, h->nb, dim, w.ff1_w);
+      d.epi = E2B_EPI_GEGLU; d.bias = w.ff1_b; d.out = h->hb; d.ldo = h->inner;
+      CK(e2b_gemm_launch(&d, st));
+    }
+    {
+      e2b_gemm_desc d = gd(M, dim, h->inner, h->hb, h->inner, w.ff2_w);
+      d.epi = E2B_EPI_RESID; d.bias = w.ff2_b;
+      d.out = h->x[0]; d.ldo = dim; d.resid = h->x[0]; d.ldr = dim;
+      d.gate = G(l, 5); d.gate_bstride = gam.bstride; d.rows_per_batch = h->N;
+      d.out_b16 = h->xb; d.ldo_b16 = dim;
+      CK(e2b_gemm_launch(&d, st));
+    }
+  }
+  return 0;
+}
+
+// x/text/frames streams from the sampler state: proj_in(y)+abs_pos, CLIP (dropped per pass), precomputed roll stream.
+int init_streams_from_state(e2b_handle* h, cudaStream_t st) {
+  const e2b_config& c = h->cfg;
+  const int R = c.num_registers;
+  CK(e2b_init_stream_launch(h->x[0], h->xb, h->registers, nullptr, -1, nullptr, nullptr, h->Bt, h->n, R, c.dim, st));
+  e2b_gemm_desc d = gd((size_t)h->Bt * h->n, c.dim, c.num_channels, h->ybf, c.num_channels, h->proj_in_w);
+  d.epi = E2B_EPI_F32; d.bias = h->proj_in_b;
+  d.out = h->x[0]; d.ldo = c.dim; d.out_b16 = h->xb; d.ldo_b16 = c.dim;
+  d.rpb_in = h->n; d.rpb_out = h->N; d.row_off = R;
+  d.add_table = h->abs_pos; d.ld_add = c.dim;
+  CK(e2b_gemm_launch(&d, st));
+  CK(e2b_init_stream_launch(h->text[0], nullptr, h->t_registers, h->clip, h->B, h->drop_clip_dev, nullptr, h->Bt, h->n, R, c.dim_text, st));
+  CU(cudaMemcpyAsync(h->frames[0], h->fr0, h->M * c.dim_frames * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int pred_head(e2b_handle* h, float* pred, cudaStream_t st) {
+  const e2b_config& c = h->cfg;
+  CK(e2b_rmsnorm_launch(h->x[0], c.dim, h->finalb, c.dim, h->final_g, 0, h->Bt, h->N, c.num_registers, c.dim, 0, st));
+  e2b_gemm_desc d = gd((size_t)h->Bt * h->n, c.num_channels, c.dim, h->finalb, c.dim, h->to_pred_w);
+  d.epi = E2B_EPI_F32; d.bias = h->to_pred_b; d.out = pred; d.ldo = c.num_channels;
+  CK(e2b_gemm_launch(&d, st));
+  return 0;
+}
+
+int set_ctx(e2b_handle* h, const float* ctx_dev, const int* ctx_lens_host, cudaStream_t st) {
+  const e2b_config& c = h->cfg;
+  std::vector<int> cl(h->B);
+  for (int b = 0; b < h->B; ++b) {
+    cl[b] = ctx_lens_host ? ctx_lens_host[b] : h->nc;
+    if (cl[b] < 0 || cl[b] > h->nc) return fail(h, "ctx_lens[%d]=%d outside [0,%d]", b, cl[b], h->nc);
+  }
+  CU(cudaMemcpyAsync(h->ctx_lens_dev, cl.data(), h->B * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(e2b_cast_pad_launch(ctx_dev, c.dim, h->ctxb, c.dim, h->B * h->nc, c.dim, st));
+  for (int l = 0; l < c.depth; ++l) {
+    // k2 = rope(to_k(ctx)) at positions N-nc..N-1 (x-transformers uses the LAST nc rows of the table), v2 = to_v(ctx)
+    e2b_gemm_desc d = gd((size_t)h->B * h->nc, 2 * h->HD, c.dim, h->ctxb, c.dim, h->L[l].kv2_w);
+    d.epi = E2B_EPI_QKV;
+    d.out = h->k2[l]; d.ldo = h->HD;
+    d.q_end = 0; d.k_end = h->HD; d.v_end = 2 * h->HD;
+    d.q_scale = 1.0f;
+    d.rope = h->rope; d.pos_off = h->N - h->nc; d.rows_per_batch = h->nc;
+    d.vt = h->vt2[l]; d.vt_ld = h->ncpad; d.heads_v = c.heads;
+    CK(e2b_gemm_launch(&d, st));
+  }
+  CU(cudaStreamSynchronize(st));   // cl (host vector) must outlive the async copy
+  return 0;
+}
+
+int set_lens(e2b_handle* h, const int* lens_host, cudaStream_t st) {
+  std::vector<int> lv(h->Bt);
+  for (int b = 0; b < h->Bt; ++b) {
+    const int l = lens_host ? lens_host[b % h->B] : h->n;
+    if (l < 0 || l > h->n) return fail(h, "lens[%d]=%d outside [0,%d]", b % h->B, l, h->n);
+    lv[b] = l + h->cfg.num_registers;
+  }
+  CU(cudaMemcpyAsync(h->lens_dev, lv.data(), h->Bt * sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================== C-ABI
+extern "C" const char* e2b_last_error(e2b_handle* h) { return h ? h->err.c_str() : g_api_err; }
+
+extern "C" int e2b_create(const e2b_config* cfg, e2b_handle** out) {
+  e2b_handle* h = nullptr;
+  if (!cfg || !out) return fail(h, "e2b_create: null argument");
+  if (cfg->dim_head != 64) return fail(h, "e2b_create: dim_head must be 64 (got %d)", cfg->dim_head);
+  if (cfg->depth < 2 || cfg->depth % 2) return fail(h, "e2b_create: depth must be even");
+  if (cfg->dim % 64 || cfg->dim_text % 64 || cfg->dim_frames % 64 || cfg->num_channels % 64)
+    return fail(h, "e2b_create: dim/dim_text/dim_frames/num_channels must be multiples of 64");
+  if (cfg->notes <= 0 || cfg->notes > 64) return fail(h, "e2b_create: notes must be in (0,64]");
+  if (cfg->kernel_size != 31) return fail(h, "e2b_create: kernel_size must be 31");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(h, "e2b_create: no CUDA device (this library has no CPU path)");
+  h = new e2b_handle();
+  h->cfg = *cfg;
+  h->HD = cfg->heads * 64; h->HDt = cfg->heads * 64; h->HDf = cfg->frames_heads * 64;
+  h->inner = cfg->dim * cfg->ff_mult; h->inner_t = cfg->dim_text * cfg->ff_mult; h->inner_f = cfg->dim_frames * cfg->ff_mult;
+  h->nmat = cfg->depth * 6;
+  *out = h;
+  return 0;
+}
+
+extern "C" void e2b_destroy(e2b_handle* h) {
+  if (!h) return;
+  free_workspace(h);
+  free_pool(h->wallocs);
+  delete h;
+}
+
+extern "C" long long e2b_launch_count(e2b_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int e2b_load_weights(e2b_handle* h, const e2b_tensor* tensors, int n, e2b_stream stream) {
+  if (!h) return fail(h, "null handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  const e2b_config& c = h->cfg;
+  free_pool(h->wallocs);
+  h->weights_loaded = false;
+  WMap w;
+  for (int i = 0; i < n; ++i) w.m[tensors[i].name] = &tensors[i];
+  const std::string T = "transformer.";
+  const int dim = c.dim, dt = c.dim_text, df = c.dim_frames, H = c.heads, HD = h->HD;
+
+  if (copy_f32(h, w, T + "registers", &h->registers, c.num_registers, dim, st)) return -1;
+  if (copy_f32(h, w, T + "text_registers", &h->t_registers, c.num_registers, dt, st)) return -1;
+  if (copy_f32(h, w, T + "frames_registers", &h->f_registers, c.num_registers, df, st)) return -1;
+  if (copy_f32(h, w, T + "abs_pos_emb.weight", &h->abs_pos, c.max_seq_len, dim, st)) return -1;
+  if (copy_f32(h, w, T + "final_norm.g", &h->final_g, dim, -1, st)) return -1;
+  if (copy_f32(h, w, T + "time_cond_mlp.0.weights", &h->fourier_w, dim / 2, -1, st)) return -1;
+  if (copy_f32(h, w, T + "time_cond_mlp.1.weight", &h->time_w1, dim, dim + 1, st)) return -1;
+  if (copy_f32(h, w, T + "time_cond_mlp.1.bias", &h->time_b1, dim, -1, st)) return -1;
+  if (pack_linear(h, w, "proj_in.weight", &h->proj_in_w, dim, c.num_channels, st)) return -1;
+  if (copy_f32(h, w, "proj_in.bias", &h->proj_in_b, dim, -1, st)) return -1;
+  if (pack_linear(h, w, "to_pred.weight", &h->to_pred_w, c.num_channels, dim, st)) return -1;
+  if (copy_f32(h, w, "to_pred.bias", &h->to_pred_b, c.num_channels, -1, st)) return -1;
+  if (pack_linear(h, w, "proj_frames.weight", &h->pf_w, df, c.notes, st, 64)) return -1;   // K padded 51 -> 64 with zeros
+  if (copy_f32(h, w, "proj_frames.bias", &h->pf_b, df, -1, st)) return -1;
+
+  // RoPE table from the (shared) inv_freq buffer: cos/sin(pos * inv_freq[j]) in fp32 like the reference
+  {
+    const e2b_tensor* t;
+    if (need(h, w, T + "rotary_emb.inv_freq", &t, 32)) return -1;
+    float inv[32];
+    CU(cudaMemcpy(inv, t->dev, sizeof(inv), cudaMemcpyDeviceToHost));
+    h->rope_rows = c.max_seq_len + c.num_registers;
+    std::vector<float> tab((size_t)h->rope_rows * 64);
+    for (int p = 0; p < h->rope_rows; ++p)
+      for (int j = 0; j < 32; ++j) {
+        const float f = (float)p * inv[j];
+        tab[((size_t)p * 32 + j) * 2] = cosf(f);
+        tab[((size_t)p * 32 + j) * 2 + 1] = sinf(f);
+      }
+    DA(h->wallocs, h->rope, tab.size());
+    CU(cudaMemcpy(h->rope, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+  }
+
+  h->L.assign(c.depth, LayerW());
+  std::vector<const float*> tmw(h->nmat), tmb(h->nmat);
+  std::vector<int> tma(h->nmat);
+  for (int l = 0; l < c.depth; ++l) {
+    LayerW& Lw = h->L[l];
+    const std::string a = T + "layers." + std::to_string(l) + ".0.";
+    const std::string x = T + "layers." + std::to_string(l) + ".1.";
+    const std::string f = T + "layers." + std::to_string(l) + ".2.";
+    if (l >= c.depth / 2 && pack_linear(h, w, a + "0.weight", &Lw.skip_w, dim, 2 * dim, st)) return -1;
+    if (pack_conv(h, w, a + "1", dim, &Lw.conv_w, &Lw.conv_b, st)) return -1;
+    if (pack_concat(h, w, {{a + "3.to_q.weight", HD}, {a + "3.to_k.weight", HD}, {a + "3.to_v.weight", HD}, {a + "3.to_v_head_gate.weight", H}}, dim,
+                    &Lw.qkv_w, st)) return -1;
+    if (copy_f32(h, w, a + "3.to_v_head_gate.bias", &Lw.hg_b, H, -1, st)) return -1;
+    if (pack_linear(h, w, a + "3.to_out.weight", &Lw.out_w, dim, HD, st)) return -1;
+    if (pack_concat(h, w, {{a + "6.to_q.weight", HD}, {a + "6.to_v_head_gate.weight", H}}, dim, &Lw.q2_w, st)) return -1;
+    if (copy_f32(h, w, a + "6.to_v_head_gate.bias", &Lw.hg2_b, H, -1, st)) return -1;
+    if (pack_concat(h, w, {{a + "6.to_k.weight", HD}, {a + "6.to_v.weight", HD}}, dim, &Lw.kv2_w, st)) return -1;
+    if (pack_linear(h, w, a + "6.to_out.weight", &Lw.out2_w, dim, HD, st)) return -1;
+    if (pack_geglu(h, w, a + "9.ff.0.proj", dim, h->inner, &Lw.ff1_w, &Lw.ff1_b, st)) return -1;
+    if (pack_linear(h, w, a + "9.ff.2.weight", &Lw.ff2_w, dim, h->inner, st)) return -1;
+    if (copy_f32(h, w, a + "9.ff.2.bias", &Lw.ff2_b, dim, -1, st)) return -1;
+    // time-conditioning matrices stay fp32: 0 norm1, 1 adaln1, 2 norm2, 3 adaln2, 4 norm3, 5 adaln3
+    const int idx[6] = {2, 4, 5, 7, 8, 10};
+    for (int k = 0; k < 6; ++k) {
+      float *wp = nullptr, *bp = nullptr;
+      const std::string base = a + std::to_string(idx[k]) + ".to_gamma";
+      if (copy_f32(h, w, base + ".weight", &wp, dim, dim, st)) return -1;
+      if (k % 2 == 1 && copy_f32(h, w, base + ".bias", &bp, dim, -1, st)) return -1;
+      tmw[l * 6 + k] = wp; tmb[l * 6 + k] = bp; tma[l * 6 + k] = k % 2;
+    }
+    if (pack_stream(h, w, x, dt, H, h->inner_t, Lw.t, st)) return -1;
+    if (pack_stream(h, w, f, df, c.frames_heads, h->inner_f, Lw.f, st)) return -1;
+    if (pack_linear(h, w, x + "5.text_frames_to_audio.weight", &Lw.tfa_w, dim, dim + dt + df, st)) return -1;
+    if (l < c.depth - 1) {
+      if (pack_linear(h, w, x + "5.audio_to_text.weight", &Lw.at_w, dt, dim + dt, st)) return -1;
+      if (pack_linear(h, w, x + "5.audio_to_frames.weight", &Lw.af_w, df, dim + df, st)) return -1;
+    }
+  }
+  DA(h->wallocs, h->tm_w, h->nmat);
+  DA(h->wallocs, h->tm_b, h->nmat);
+  DA(h->wallocs, h->tm_act, h->nmat);
+  CU(cudaMemcpy(h->tm_w, tmw.data(), h->nmat * sizeof(float*), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->tm_b, tmb.data(), h->nmat * sizeof(float*), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->tm_act, tma.data(), h->nmat * sizeof(int), cudaMemcpyHostToDevice));
+  CU(cudaStreamSynchronize(st));
+  h->weights_loaded = true;
+  return 0;
+}
+
+extern "C" int e2b_prepare(e2b_handle* h, int B, int n, int nc, int P) {
+  if (!h) return fail(h, "null handle");
+  const e2b_config& c = h->cfg;
+  if (B <= 0 || n <= 0 || nc <= 0 || P < 1 || P > 8) return fail(h, "e2b_prepare: bad shape B=%d n=%d nc=%d P=%d", B, n, nc, P);
+  if (n > c.max_seq_len) return fail(h, "e2b_prepare: n=%d exceeds max_seq_len=%d", n, c.max_seq_len);   // X3:958
+  if (B == h->B && n == h->n && nc == h->nc && P == h->P) return 0;
+  free_workspace(h);
+  h->B = B; h->n = n; h->nc = nc; h->P = P; h->Pctx = P;
+  h->N = n + c.num_registers; h->Bt = B * P; h->M = (size_t)h->Bt * h->N;
+  h->Npad = rup(h->N, 8); h->ncpad = rup(nc, 8);
+  if (nc > h->N) return fail(h, "e2b_prepare: nc=%d exceeds sequence length %d", nc, h->N);
+  const size_t M = h->M;
+  const int dim = c.dim, dt = c.dim_text, df = c.dim_frames;
+  const int Cmax = std::max(dim, std::max(dt, df));
+  const int HDmax = std::max(h->HD, h->HDf), Hmax = std::max(c.heads, c.frames_heads);
+  const int inner_max = std::max(h->inner, std::max(h->inner_t, h->inner_f));
+  for (int i = 0; i < 2; ++i) {
+    DA(h->sallocs, h->x[i], M * dim);
+    DA(h->sallocs, h->text[i], M * dt);
+    DA(h->sallocs, h->frames[i], M * df);
+  }
+  DA(h->sallocs, h->xb, M * dim);
+  DA(h->sallocs, h->textb, M * dt);
+  DA(h->sallocs, h->framesb, M * df);
+  DA(h->sallocs, h->xtmpb, M * dim);
+  h->skipb.resize(c.depth / 2);
+  for (auto& p : h->skipb) DA(h->sallocs, p, M * dim);
+  DA(h->sallocs, h->nb, M * Cmax);
+  DA(h->sallocs, h->qk, M * 2 * HDmax);
+  DA(h->sallocs, h->vt, (size_t)h->Bt * Hmax * 64 * h->Npad);
+  DA(h->sallocs, h->hg, M * Hmax);
+  DA(h->sallocs, h->ob, M * HDmax);
+  DA(h->sallocs, h->hb, M * inner_max);
+  DA(h->sallocs, h->ybf, (size_t)h->Bt * n * c.num_channels);
+  DA(h->sallocs, h->finalb, (size_t)h->Bt * n * dim);
+  DA(h->sallocs, h->fin, (size_t)h->Bt * n * 64);
+  DA(h->sallocs, h->ctxb, (size_t)B * nc * dim);
+  h->k2.resize(c.depth);
+  h->vt2.resize(c.depth);
+  for (int l = 0; l < c.depth; ++l) {
+    DA(h->sallocs, h->k2[l], (size_t)B * nc * h->HD);
+    DA(h->sallocs, h->vt2[l], (size_t)B * c.heads * 64 * h->ncpad);
+  }
+  DA(h->sallocs, h->fr0, M * df);
+  DA(h->sallocs, h->clip, (size_t)B * n * dt);
+  DA(h->sallocs, h->pred, (size_t)h->Bt * n * c.num_channels);
+  h->gam_capacity = std::max(1024, h->Bt);
+  DA(h->sallocs, h->gam, (size_t)h->gam_capacity * h->nmat * dim);
+  DA(h->sallocs, h->tcond, (size_t)h->gam_capacity * dim);
+  DA(h->sallocs, h->times_dev, h->gam_capacity);
+  DA(h->sallocs, h->apg_scratch, 2 * B);
+  DA(h->sallocs, h->lens_dev, h->Bt);
+  DA(h->sallocs, h->ctx_lens_dev, B);
+  DA(h->sallocs, h->drop_clip_dev, h->Bt);
+  return 0;
+}
+
+extern "C" int e2b_set_conditions(e2b_handle* h, const float* clip_dev, const float* roll_dev, const float* ctx_dev, const int* lens_host,
+                                  const int* ctx_lens_host, const int* pass_flags_host, e2b_stream stream) {
+  if (!h) return fail(h, "null handle");
+  if (!h->weights_loaded) return fail(h, "e2b_set_conditions: weights not loaded");
+  if (!h->B) return fail(h, "e2b_set_conditions: call e2b_prepare first");
+  if (!clip_dev || !ctx_dev) return fail(h, "e2b_set_conditions: clip and ctx are required");
+  cudaStream_t st = (cudaStream_t)stream;
+  const e2b_config& c = h->cfg;
+  const int R = c.num_registers;
+  // passes: pass 0 = full conditioning; context-live passes must come first (their cross-attention is batched)
+  int pctx = 0;
+  bool seen_dropped = false;
+  std::vector<unsigned char> dc(h->Bt);
+  for (int p = 0; p < h->P; ++p) {
+    const int fl = pass_flags_host ? pass_flags_host[p] : (p == 0 ? 0 : (E2B_DROP_CLIP | E2B_DROP_CTX));
+    if (p == 0 && fl != 0) return fail(h, "pass 0 must keep every condition");
+    if (fl & E2B_DROP_CTX) seen_dropped = true;
+    else {
+      if (seen_dropped) return fail(h, "passes that keep the T5 context must precede passes that drop it");
+      ++pctx;
+    }
+    h->pass_flags[p] = fl;
+    for (int b = 0; b < h->B; ++b) dc[p * h->B + b] = (fl & E2B_DROP_CLIP) ? 1 : 0;
+  }
+  h->Pctx = pctx;
+  CU(cudaMemcpyAsync(h->drop_clip_dev, dc.data(), h->Bt, cudaMemcpyHostToDevice, st));
+  if (set_lens(h, lens_host, st)) return -1;
+  CU(cudaMemcpyAsync(h->clip, clip_dev, (size_t)h->B * h->n * c.dim_text * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // piano-roll stream: proj_frames (K padded to 64) + registers, per pass (roll dropped => proj_frames(0) = bias)
+  const size_t per_pass = (size_t)h->B * h->n;
+  for (int p = 0; p < h->P; ++p) {
+    bf16* dst = h->fin + p * per_pass * 64;
+    if (roll_dev && !(h->pass_flags[p] & E2B_DROP_ROLL)) CK(e2b_cast_pad_launch(roll_dev, c.notes, dst, 64, (int)per_pass, c.notes, st));
+    else CU(cudaMemsetAsync(dst, 0, per_pass * 64 * sizeof(bf16), st));
+  }
+  CK(e2b_init_stream_launch(h->fr0, nullptr, h->f_registers, nullptr, -1, nullptr, nullptr, h->Bt, h->n, R, c.dim_frames, st));
+  {
+    e2b_gemm_desc d = gd((size_t)h->Bt * h->n, c.dim_frames, 64, h->fin, 64, h->pf_w);
+    d.epi = E2B_EPI_F32; d.bias = h->pf_b;
+    d.out = h->fr0; d.ldo = c.dim_frames;
+    d.rpb_in = h->n; d.rpb_out = h->N; d.row_off = R;
+    CK(e2b_gemm_launch(&d, st));
+  }
+  if (set_ctx(h, ctx_dev, ctx_lens_host, st)) return -1;
+  h->conditions_set = true;
+  return 0;
+}
+
+extern "C" int e2b_forward(e2b_handle* h, const float* x_dev, float t, float* pred_dev, e2b_stream stream) {
+  if (!h) return fail(h, "null handle");
+  if (!h->conditions_set) return fail(h, "e2b_forward: call e2b_set_conditions first");
+  cudaStream_t st = (cudaStream_t)stream;
+  const e2b_config& c = h->cfg;
+  const size_t per_pass = (size_t)h->B * h->n;
+  if (compute_time_tables(h, &t, 1, st)) return -1;
+  CU(cudaStreamSynchronize(st));   // &t is a stack address
+  for (int p = 0; p < h->P; ++p)
+    CK(e2b_cast_pad_launch(x_dev, c.num_channels, h->ybf + p * per_pass * c.num_channels, c.num_channels, (int)per_pass, c.num_channels, st));
+  if (init_streams_from_state(h, st)) return -1;
+  if (forward_core(h, GamRef{h->gam, 0}, st)) return -1;
+  return pred_head(h, pred_dev, st);
+}
+
+extern "C" int e2b_sample(e2b_handle* h, float* y_dev, const float* t_grid_host, int steps, const float* guidance_w_host, int apg,
+                          float keep_parallel, e2b_stream stream) {
+  if (!h) return fail(h, "null handle");
+  if (!h->conditions_set) return fail(h, "e2b_sample: call e2b_set_conditions first");
+  if (steps < 1) return fail(h, "e2b_sample: steps must be >= 1");
+  if (steps - 1 > h->gam_capacity) return fail(h, "e2b_sample: too many steps");
+  if (h->P > 1 && !guidance_w_host) return fail(h, "e2b_sample: guidance weights required");
+  cudaStream_t st = (cudaStream_t)stream;
+  const e2b_config& c = h->cfg;
+  const size_t per_pass = (size_t)h->B * h->n;
+  const long long per_sample = (long long)h->n * c.num_channels;
+  if (steps == 1) return 0;
+  if (compute_time_tables(h, t_grid_host, steps - 1, st)) return -1;
+  for (int p = 0; p < h->P; ++p)
+    CK(e2b_cast_pad_launch(y_dev, c.num_channels, h->ybf + p * per_pass * c.num_channels, c.num_channels, (int)per_pass, c.num_channels, st));
+  for (int s = 0; s < steps - 1; ++s) {
+    const float dt = t_grid_host[s + 1] - t_grid_host[s];
+    if (init_streams_from_state(h, st)) return -1;
+    if (forward_core(h, GamRef{h->gam + (size_t)s * h->nmat * c.dim, 0}, st)) return -1;
+    if (pred_head(h, h->pred, st)) return -1;
+    CK(e2b_guided_euler_launch(y_dev, h->pred, h->P, h->B, per_sample, guidance_w_host, dt, apg, keep_parallel, h->apg_scratch, h->ybf,
+                               h->P, st));
+  }
+  return 0;
+}
+
+extern "C" int e2b_transformer_forward(e2b_handle* h, const float* x_dev, const float* times_host, const int* lens_host,
+                                       const float* text_dev, const float* frames_dev, const float* ctx_dev, const int* ctx_lens_host,
+                                       float* out_dev, e2b_stream stream) {
+  if (!h) return fail(h, "null handle");
+  if (!h->weights_loaded || !h->B) return fail(h, "e2b_transformer_forward: load weights and prepare first");
+  if (h->P != 1) return fail(h, "e2b_transformer_forward: prepare with P=1");
+  if (!x_dev || !times_host || !text_dev || !frames_dev || !ctx_dev) return fail(h, "e2b_transformer_forward: all inputs are required");
+  cudaStream_t st = (cudaStream_t)stream;
+  const e2b_config& c = h->cfg;
+  const int R = c.num_registers;
+  h->Pctx = 1;
+  if (set_lens(h, lens_host, st)) return -1;
+  if (set_ctx(h, ctx_dev, ctx_lens_host, st)) return -1;
+  if (compute_time_tables(h, times_host, h->B, st)) return -1;
+  CK(e2b_init_stream_launch(h->x[0], h->xb, h->registers, x_dev, h->B, nullptr, h->abs_pos, h->B, h->n, R, c.dim, st));
+  CK(e2b_init_stream_launch(h->text[0], nullptr, h->t_registers, text_dev, h->B, nullptr, nullptr, h->B, h->n, R, c.dim_text, st));
+  CK(e2b_init_stream_launch(h->frames[0], nullptr, h->f_registers, frames_dev, h->B, nullptr, nullptr, h->B, h->n, R, c.dim_frames, st));
+  if (forward_core(h, GamRef{h->gam, h->nmat * c.dim}, st)) return -1;
+  CK(e2b_rmsnorm_launch(h->x[0], c.dim, out_dev, c.dim, h->final_g, 0, h->B, h->N, R, c.dim, 1, st));
+  h->conditions_set = false;
+  return 0;
+}
+
+extern "C" int e2b_guided_euler(float* y_dev, const float* pred_dev, int P, int B, long long per_sample, const float* w_host, float dt,
+                                int apg, float keep_parallel, double* scratch_dev, e2b_stream stream) {
+  e2b_handle* h = nullptr;
+  if (e2b_guided_euler_launch(y_dev, pred_dev, P, B, per_sample, w_host, dt, apg, keep_parallel, scratch_dev, nullptr, 0, (cudaStream_t)stream))
+    return fail(h, "e2b_guided_euler: %s", e2b_kernel_last_error());
+  return 0;
+}
+
+extern "C" double e2b_forward_flops(e2b_handle* h) {
+  if (!h || !h->B) return 0.0;
+  const e2b_config& c = h->cfg;
+  const double N = h->N, n = h->n, nc = h->nc;
+  const double Bt = h->Bt, Bc = (double)h->Pctx * h->B;
+  auto side = [&](double C, double heads, double inner) {
+    return 2 * N * C * (3 * heads * 64 + heads) + 4 * N * N * heads * 64 + 2 * N * heads * 64 * C + 2 * N * C * 3 * inner + 2 * N * C * 31;
+  };
+  double per = 2 * n * (c.num_channels * (double)c.dim + 64.0 * c.dim_frames + (double)c.dim * c.num_channels);
+  per += c.depth * (side(c.dim_text, c.heads, h->inner_t) + side(c.dim_frames, c.frames_heads, h->inner_f));
+  per += c.depth * 2 * N * (c.dim + c.dim_text + c.dim_frames) * c.dim;
+  per += (c.depth - 1) * (2 * N * (c.dim + c.dim_text) * c.dim_text + 2 * N * (c.dim + c.dim_frames) * c.dim_frames);
+  per += (c.depth / 2) * 2 * N * 2 * c.dim * c.dim;
+  per += c.depth * (side(c.dim, c.heads, h->inner));
+  double cross = c.depth * (2 * N * c.dim * (h->HD + c.heads) + 4 * N * nc * h->HD + 2 * N * h->HD * c.dim);
+  return Bt * per + Bc * cross;
+}

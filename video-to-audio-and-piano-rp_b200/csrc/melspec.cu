@@ -1,0 +1,140 @@
+// STFT + mel front end (reference MelSpec, e2_tts_crossatt3.py:375-417 + log :293-294): torchaudio MelSpectrogram with
+// center=True / reflect padding, periodic Hann window, power=1 (magnitude), HTK mel filterbank without norm, then
+// log(clamp(x, 1e-5)).  One CTA transforms FR consecutive frames of one clip: windowed frame -> shared memory
+// (bit-reversed) -> in-place radix-2 FFT -> |X| -> filterbank dot products -> log -> [B, n_mels, T] tile store.
+#include <math.h>
+
+#include <map>
+#include <vector>
+
+#include "../../include/e2b.h"
+#include "kernels.h"
+
+namespace e2b {
+
+constexpr int MEL_THREADS = 256;
+constexpr int MEL_FR = 8;        // frames per CTA (one 32-byte output segment per mel row)
+
+__global__ void __launch_bounds__(MEL_THREADS) melspec_kernel(const float* __restrict__ wav, int nw, int n_fft, int log2n, int hop,
+                                                              int n_mels, int T, const float* __restrict__ window,
+                                                              const float* __restrict__ fb, const float2* __restrict__ tw,
+                                                              float* __restrict__ out, float log_eps) {
+  extern __shared__ float sm[];
+  float2* z = reinterpret_cast<float2*>(sm);          // n_fft complex
+  float* mag = sm + 2 * n_fft;                        // n_fft/2 + 1
+  float* tile = mag + (n_fft / 2 + 1);                // n_mels * MEL_FR
+  float* part = tile + n_mels * MEL_FR;               // MEL_THREADS partial sums
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * MEL_FR;
+  const float* x = wav + (size_t)b * nw;
+  const int nbins = n_fft / 2 + 1;
+  const int half = n_fft / 2;
+
+  for (int fr = 0; fr < MEL_FR; ++fr) {
+    const int t = t0 + fr;
+    if (t >= T) break;      // uniform
+    const int start = t * hop - half;
+    for (int i = threadIdx.x; i < n_fft; i += MEL_THREADS) {
+      int s = start + i;
+      if (s < 0) s = -s;
+      if (s >= nw) s = 2 * (nw - 1) - s;
+      const int r = __brev((unsigned)i) >> (32 - log2n);
+      z[r] = make_float2(x[s] * window[i], 0.f);
+    }
+    __syncthreads();
+    for (int st = 0; st < log2n; ++st) {
+      const int hs = 1 << st;                         // half butterfly span
+      for (int j = threadIdx.x; j < half; j += MEL_THREADS) {
+        const int grp = j >> st, k = j & (hs - 1);
+        const int i0 = (grp << (st + 1)) + k, i1 = i0 + hs;
+        const float2 w = tw[k << (log2n - 1 - st)];   // exp(-2 pi i k / (2 hs))
+        const float2 a = z[i0], c = z[i1];
+        const float2 wc = make_float2(c.x * w.x - c.y * w.y, c.x * w.y + c.y * w.x);
+        z[i0] = make_float2(a.x + wc.x, a.y + wc.y);
+        z[i1] = make_float2(a.x - wc.x, a.y - wc.y);
+      }
+      __syncthreads();
+    }
+    for (int k = threadIdx.x; k < nbins; k += MEL_THREADS) mag[k] = sqrtf(z[k].x * z[k].x + z[k].y * z[k].y);
+    __syncthreads();
+    // filterbank: split the bins over `ways` thread groups per mel
+    const int ways = MEL_THREADS / n_mels > 0 ? MEL_THREADS / n_mels : 1;
+    for (int m0 = 0; m0 < n_mels; m0 += MEL_THREADS) {
+      const int m = m0 + (threadIdx.x % (n_mels < MEL_THREADS ? n_mels : MEL_THREADS));
+      const int way = threadIdx.x / (n_mels < MEL_THREADS ? n_mels : MEL_THREADS);
+      float acc = 0.f;
+      if (m < n_mels && way < ways) {
+        const int per = (nbins + ways - 1) / ways;
+        const int k0 = way * per, k1 = min(nbins, k0 + per);
+        for (int k = k0; k < k1; ++k) acc = fmaf(mag[k], __ldg(fb + (size_t)k * n_mels + m), acc);
+      }
+      part[threadIdx.x] = acc;
+      __syncthreads();
+      if (m < n_mels && way == 0) {
+        float s = 0.f;
+        for (int wy = 0; wy < ways; ++wy) s += part[wy * (n_mels < MEL_THREADS ? n_mels : MEL_THREADS) + (m - m0)];
+        tile[m * MEL_FR + fr] = logf(fmaxf(s, log_eps));
+      }
+      __syncthreads();
+    }
+  }
+  const int nfr = min(MEL_FR, T - t0);
+  for (int i = threadIdx.x; i < n_mels * MEL_FR; i += MEL_THREADS) {
+    const int m = i / MEL_FR, fr = i % MEL_FR;
+    if (fr < nfr) out[((size_t)b * n_mels + m) * T + t0 + fr] = tile[i];
+  }
+}
+
+static std::map<int, float2*> g_twiddles;
+
+static float2* twiddles_for(int n_fft) {
+  auto it = g_twiddles.find(n_fft);
+  if (it != g_twiddles.end()) return it->second;
+  std::vector<float2> h(n_fft / 2);
+  for (int k = 0; k < n_fft / 2; ++k) {
+    const double a = -2.0 * M_PI * (double)k / (double)n_fft;
+    h[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  float2* d = nullptr;
+  if (cudaMalloc(&d, h.size() * sizeof(float2)) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  g_twiddles[n_fft] = d;
+  return d;
+}
+
+}  // namespace e2b
+
+using namespace e2b;
+
+extern "C" int e2b_melspec_launch(const float* wav, int B, int nw, int n_fft, int hop, int n_mels, const float* window, const float* fb,
+                                  const float* twiddle, float* out, float log_eps, cudaStream_t stream) {
+  int log2n = 0;
+  while ((1 << log2n) < n_fft) ++log2n;
+  if ((1 << log2n) != n_fft || n_fft < 64 || n_fft > 4096) { e2b_set_kernel_error("melspec: n_fft=%d must be a power of two in [64,4096]", n_fft); return -1; }
+  if (nw <= n_fft / 2) { e2b_set_kernel_error("melspec: waveform shorter than the reflect padding"); return -1; }
+  if (n_mels <= 0 || B <= 0 || hop <= 0) { e2b_set_kernel_error("melspec: bad arguments"); return -1; }
+  const int T = nw / hop + 1;
+  const size_t smem = (2 * n_fft + n_fft / 2 + 1 + n_mels * MEL_FR + MEL_THREADS) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    if (cudaFuncSetAttribute(melspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      e2b_set_kernel_error("melspec: shared memory request %zu failed", smem);
+      return -1;
+    }
+    configured = smem;
+  }
+  dim3 grid((T + MEL_FR - 1) / MEL_FR, B);
+  melspec_kernel<<<grid, MEL_THREADS, smem, stream>>>(wav, nw, n_fft, log2n, hop, n_mels, T, window, fb,
+                                                      reinterpret_cast<const float2*>(twiddle), out, log_eps);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { e2b_set_kernel_error("melspec launch: %s", cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+
+extern "C" int e2b_melspec(const float* wav_dev, int B, int nw, int n_fft, int hop, int n_mels, const float* window_dev,
+                           const float* fb_dev, float* out_dev, e2b_stream stream) {
+  float2* tw = twiddles_for(n_fft);
+  if (!tw) { e2b_set_kernel_error("melspec: twiddle table allocation failed"); return -1; }
+  return e2b_melspec_launch(wav_dev, B, nw, n_fft, hop, n_mels, window_dev, fb_dev, reinterpret_cast<const float*>(tw), out_dev, 1e-5f,
+                            (cudaStream_t)stream);
+}
