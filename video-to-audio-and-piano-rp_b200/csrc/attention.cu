@@ -12,41 +12,40 @@
 // RoPE-rotated, k RoPE-rotated, V transposed ([d, keys]) -- all produced by the QKV GEMM epilogue (gemm.cu) -- so
 // both MMAs take plain K-major operands.
 #include "kernels.h"
+#include "prof.h"
 #include "ptx.cuh"
 
 namespace e2b {
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
-constexpr int ATT_THREADS = 256;
+constexpr int ATT_THREADS = 384;           // warps 0-3: TMA / MMA / TMEM alloc / spare ; warps 4-11: softmax + epilogue
 constexpr int ATT_BQ = 128, ATT_BK = 128, ATT_D = 64;
 constexpr int ATT_SQ = 0;                       // 16 KB  Q   [128 q, 64 d]
 constexpr int ATT_SK = 16384;                   // 2 x 16 KB  K   [128 keys, 64 d]
 constexpr int ATT_SV = ATT_SK + 2 * 16384;      // 2 x 16 KB  V^T 2 x [64 d, 64 keys]
 constexpr int ATT_SP = ATT_SV + 2 * 16384;      // 2 x 32 KB  P   2 x [128 q, 64 keys]
-constexpr int ATT_BAR = ATT_SP + 2 * 32768;
+constexpr int ATT_LSUM = ATT_SP + 2 * 32768;    // 2 x 128 floats: per-row partial sums of the two column halves
+constexpr int ATT_BAR = ATT_LSUM + 1024;
 constexpr int ATT_SMEM = ATT_BAR + 256 + 1024;
 constexpr uint32_t ATT_TMEM_COLS = 512;         // S0 @0, S1 @128, O @256
 
-// tanh(x) for the soft-clamp.  |x| = |logit|/50 is small for realistic logits, so an odd polynomial on the FMA pipe
-// (abs error < 5e-6 for |x| < 0.5) replaces the MUFU op (tanh.approx.f32 is only 2^-11 accurate, which the following
-// exp would amplify 50x); larger arguments take the exact exp-based form.
-__device__ __forceinline__ float softclamp_unit(float x) {
-  const float x2 = x * x;
-  if (x2 < 0.25f) {
-    float p = fmaf(x2, 62.0f / 2835.0f, -17.0f / 315.0f);
-    p = fmaf(x2, p, 2.0f / 15.0f);
-    p = fmaf(x2, p, -1.0f / 3.0f);
-    p = fmaf(x2, p, 1.0f);
-    return x * p;
-  }
+// Soft-clamp + exponent in one polynomial.  With w = z^2 and |z| / clamp < 0.5,
+//   log2(e) * clamp * tanh(z / clamp) = z * (c0 + w (c1 + w (c2 + w (c3 + w c4))))     (abs. error < 3e-4 in the exponent
+// at the edge, < 1e-5 for |z/clamp| < 0.3), i.e. 6 FMA-pipe ops and ONE MUFU (ex2) per logit instead of tanh.approx (only
+// 2^-11 accurate, amplified 50x by the exp) + ex2.  Larger logits (rare) take the exact exp-based tanh.
+struct ClampPoly { float c0, c1, c2, c3, c4, wmax, clamp; };
+
+__device__ __forceinline__ float softclamp_exp2_arg_exact(float z, float clamp) {
+  const float x = z / clamp;
   const float e = ex2_approx(x * 2.8853900817779268f);     // exp(2x)
-  return 1.0f - __fdividef(2.0f, 1.0f + e);
+  return (1.0f - __fdividef(2.0f, 1.0f + e)) * clamp * 1.4426950408889634f;
 }
 
 struct AttnArgs {
   CUtensorMap tmQ, tmK, tmV;
   e2b_attn_desc d;
+  ClampPoly cp;
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_constant__ AttnArgs args) {
@@ -57,8 +56,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   uint64_t* kv_full = bars + 1;     // [2]
   uint64_t* kv_empty = bars + 3;    // [2]
   uint64_t* s_full = bars + 5;      // [2]
-  uint64_t* s_empty = bars + 7;     // [2] (128 arrivals)
-  uint64_t* p_full = bars + 9;      // [2] (128 arrivals)
+  uint64_t* s_empty = bars + 7;     // [2] (256 arrivals)
+  uint64_t* p_full = bars + 9;      // [2] (256 arrivals)
   uint64_t* p_empty = bars + 11;    // [2]
   uint64_t* o_full = bars + 13;     // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
@@ -84,8 +83,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 128);
-      mbar_init(&p_full[s], 128);
+      mbar_init(&s_empty[s], 256);
+      mbar_init(&p_full[s], 256);
       mbar_init(&p_empty[s], 1);
     }
     fence_mbar_init();
@@ -151,17 +150,19 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     }
     umma_commit(o_full);
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ softmax + epilogue (thread = query row)
-    const int ew = warp - 4;
-    const int r = ew * 32 + lane;                       // row inside the tile == TMEM lane
+    // ------------------------------------------------------------ softmax + epilogue
+    // 8 warps: warp (4 + q) and (8 + q) both own TMEM lane quarter q (= query rows 32q..32q+31); the first group handles
+    // key columns 0-63 of every S tile, the second 64-127 (ncu on the 4-warp version: issue-limited, 12 % warps active).
+    const int sw = warp - 4;
+    const int quarter = sw & 3, half = sw >> 2;
+    const int r = quarter * 32 + lane;                  // row inside the tile == TMEM lane
     const int q_pos = qt * ATT_BQ + r;
     const bool q_valid = q_pos < d.q_rows_per_batch;
-    const bool warp_valid = (qt * ATT_BQ + ew * 32) < d.q_rows_per_batch;
-    const uint32_t lane_base = uint32_t(ew * 32) << 16;
-    const float inv_clamp = 1.0f / d.softclamp;
-    const float out_scale = d.softclamp * 1.4426950408889634f;   // clamp * log2(e)
+    const bool warp_valid = (qt * ATT_BQ + quarter * 32) < d.q_rows_per_batch;
+    const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+    const ClampPoly cp = args.cp;
     const uint32_t p_row_off = (r >> 3) * 1024 + (r & 7) * 128;
-    float l = 0.f;
+    float l0 = 0.f, l1 = 0.f;
 
     for (int j = 0; j < nt; ++j) {
       const int s = j & 1;
@@ -170,32 +171,56 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       mbar_wait(&s_full[s], ph);
       tc_fence_after();
       mbar_wait(&p_empty[s], ph ^ 1);
-      uint8_t* sp = smem + ATT_SP + s * 32768;
+      uint8_t* atom = smem + ATT_SP + s * 32768 + half * 16384 + p_row_off;      // keys 64*half .. +63 of this row
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = half * 64 + cc * 32;             // first key column of this chunk inside the tile
         uint32_t pk[16];
-        if (warp_valid && c * 32 < nvalid) {
+        if (warp_valid && c0 < nvalid) {
           uint32_t v[32];
-          tmem_ld32(tmem_base + lane_base + s * ATT_BK + c * 32, v);
+          tmem_ld32(tmem_base + lane_base + s * ATT_BK + c0, v);
           tmem_ld_wait();
-          float p[32];
+          float arg[32];
+          float wm = 0.f;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float e = ex2_approx(softclamp_unit(__uint_as_float(v[i]) * inv_clamp) * out_scale);
-            p[i] = (c * 32 + i < nvalid) ? e : 0.f;
-            l += p[i];
+            const float z = __uint_as_float(v[i]);
+            const float w = z * z;
+            wm = fmaxf(wm, w);
+            float q = fmaf(w, cp.c4, cp.c3);
+            q = fmaf(w, q, cp.c2);
+            q = fmaf(w, q, cp.c1);
+            q = fmaf(w, q, cp.c0);
+            arg[i] = z * q;
+          }
+          if (__any_sync(0xffffffffu, wm >= cp.wmax)) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float z = __uint_as_float(v[i]);
+              if (z * z >= cp.wmax) arg[i] = softclamp_exp2_arg_exact(z, cp.clamp);
+            }
+          }
+          float p[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) p[i] = ex2_approx(arg[i]);
+          if (c0 + 32 > nvalid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) p[i] = (c0 + i < nvalid) ? p[i] : 0.f;
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
+          for (int i = 0; i < 16; ++i) {
+            l0 += p[2 * i];
+            l1 += p[2 * i + 1];
+            pk[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) pk[i] = 0u;
         }
-        // keys c*32 .. c*32+31 -> swizzle atom (c >> 1), 16-byte chunks ((c & 1) * 4 + q) ^ (r & 7)
-        uint8_t* atom = sp + (c >> 1) * 16384 + p_row_off;
+        // 16-byte chunks (cc*4 + q) of the 128-byte swizzled row
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
+          const int chunk = (cc * 4 + q) ^ (r & 7);
           *reinterpret_cast<uint4*>(atom + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
       }
@@ -205,6 +230,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       mbar_arrive(&p_full[s]);
     }
 
+    // combine the two column halves' row sums
+    float* lsum = reinterpret_cast<float*>(smem + ATT_LSUM);
+    lsum[half * 128 + r] = l0 + l1;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l = lsum[r] + lsum[128 + r];
+
     mbar_wait(o_full, 0);
     tc_fence_after();
     float scale = 0.f;
@@ -212,14 +243,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       scale = 1.0f / l;
       if (d.hgate) scale *= __ldg(d.hgate + (size_t)(b * d.q_rows_per_batch + q_pos) * d.hgate_ld + h);
     }
-    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)(b * d.q_rows_per_batch + q_pos) * d.ldo + h * ATT_D;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)(b * d.q_rows_per_batch + q_pos) * d.ldo + h * ATT_D + half * 32;
+    {
       uint32_t v[32];
-      tmem_ld32(tmem_o + lane_base + c * 32, v);
+      tmem_ld32(tmem_o + lane_base + half * 32, v);
       tmem_ld_wait();
       if (q_valid) {
-        uint4* o4 = reinterpret_cast<uint4*>(op + c * 32);
+        uint4* o4 = reinterpret_cast<uint4*>(op);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 u;
@@ -248,6 +278,16 @@ extern "C" int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream)
   if ((d->ldo % 8) || (reinterpret_cast<uintptr_t>(d->out) & 15)) { e2b_set_kernel_error("attention: out must be 16-byte aligned"); return -1; }
   AttnArgs a;
   a.d = *d;
+  {
+    const double L2E = 1.4426950408889634, c = d->softclamp > 0 ? d->softclamp : 50.0, c2 = c * c;
+    a.cp.c0 = (float)L2E;
+    a.cp.c1 = (float)(-L2E / (3.0 * c2));
+    a.cp.c2 = (float)(2.0 * L2E / (15.0 * c2 * c2));
+    a.cp.c3 = (float)(-17.0 * L2E / (315.0 * c2 * c2 * c2));
+    a.cp.c4 = (float)(62.0 * L2E / (2835.0 * c2 * c2 * c2 * c2));
+    a.cp.wmax = (float)(0.25 * c2);
+    a.cp.clamp = (float)c;
+  }
   const uint64_t q_rows = (uint64_t)d->batch * d->q_rows_per_batch;
   const int kv_batches = d->kv_batch_mod > 0 ? d->kv_batch_mod : d->batch;
   const uint64_t k_rows = (uint64_t)kv_batches * d->kv_rows_per_batch;
@@ -261,6 +301,9 @@ extern "C" int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream)
     configured = true;
   }
   dim3 grid((d->q_rows_per_batch + ATT_BQ - 1) / ATT_BQ, d->heads, d->batch);
+  ProfScope ps(stream, "attention", (long long)d->batch * d->q_rows_per_batch, d->kv_rows_per_batch, d->heads,
+               4.0 * d->batch * d->heads * (double)d->q_rows_per_batch * d->kv_rows_per_batch * 64.0,
+               2.0 * d->batch * d->heads * 64.0 * (2.0 * d->q_rows_per_batch + 2.0 * d->kv_rows_per_batch));
   attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { e2b_set_kernel_error("attention launch: %s", cudaGetErrorString(e)); return -1; }

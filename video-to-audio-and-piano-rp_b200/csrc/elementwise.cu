@@ -7,6 +7,7 @@
 #include <math.h>
 
 #include "kernels.h"
+#include "prof.h"
 #include "ptx.cuh"
 
 namespace e2b {
@@ -16,7 +17,7 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // ------------------------------------------------------------------------------------------------ rmsnorm
 constexpr int NORM_MAX_V4 = 16;   // C <= 2048
@@ -63,44 +64,91 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------ dwconv
-// One thread = one channel, walking down a segment of rows with a register ring buffer (no shared memory, every
-// input element is loaded once per segment, lanes = consecutive channels so every access is a coalesced 128 B line).
-template <int KS, int PF>
-__global__ void __launch_bounds__(128) dwconv_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ wt,
-                                                     const float* __restrict__ bias, const int* __restrict__ lens, int N, int C, int seg) {
-  constexpr int HALF = KS / 2, RS = KS + PF;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const int b = blockIdx.z;
-  const int r0 = blockIdx.y * seg;
-  const int r1 = min(N, r0 + seg);
-  const int len = lens ? min(N, __ldg(lens + b)) : N;
-  const float* xb = x + (size_t)b * N * C + c;
-  float* yb = y + (size_t)b * N * C + c;
-  float w[KS];
+// y = x + mask * silu(conv31(mask * x) + bias), channels-last.  TMA-fed: a persistent CTA streams [64+30 rows x 128
+// channels] fp32 tiles of x into a double-buffered shared-memory ring (3-D tensor map over [batch, N, C]: rows outside
+// the sequence are zero-filled by the TMA unit, which is exactly the conv's zero padding).  One thread = one channel;
+// it slides an 8-output register window down the tile, so every x element is read from shared memory once and feeds
+// 31 FMAs with 8 independent accumulators.  (The first version -- global loads into a register ring -- was latency
+// bound: ncu 8 % DRAM, long-scoreboard 4.3 stalls/issue.)
+constexpr int DW_T = 64;            // output rows per tile
+constexpr int DW_C = 128;           // channels per tile == threads per CTA
+constexpr int DW_G = 8;             // outputs per register-window step
+
+int make_tmap_generic(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims, const uint64_t* strides,
+                      const uint32_t* box);
+
+template <int KS>
+__global__ void __launch_bounds__(DW_C) dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmx, float* __restrict__ y,
+                                                          const float* __restrict__ wt, const float* __restrict__ bias,
+                                                          const int* __restrict__ lens, int batch, int N, int C) {
+  constexpr int HALO = KS - 1, HALF = KS / 2, ROWS = DW_T + HALO;
+  extern __shared__ uint8_t smem_raw[];
+  float* buf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));   // 2 x [ROWS][DW_C]
+  __shared__ uint64_t full[2];
+  const int tid = threadIdx.x;
+  const int cchunks = (C + DW_C - 1) / DW_C, rtiles = (N + DW_T - 1) / DW_T;
+  const int total = batch * rtiles * cchunks;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmx);
+  }
+  __syncthreads();
+  auto issue = [&](int tile, int s) {
+    const int cc = tile % cchunks, rt = (tile / cchunks) % rtiles, b = tile / (cchunks * rtiles);
+    mbar_arrive_expect_tx(&full[s], ROWS * DW_C * 4);
+    tma_load_3d(buf + (size_t)s * ROWS * DW_C, &tmx, &full[s], cc * DW_C, rt * DW_T - HALF, b);
+  };
+  if (tid == 0 && (int)blockIdx.x < total) issue(blockIdx.x, 0);
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+    const int s = it & 1;
+    if (tid == 0 && tile + (int)gridDim.x < total) issue(tile + gridDim.x, s ^ 1);
+    const int cc = tile % cchunks, rt = (tile / cchunks) % rtiles, b = tile / (cchunks * rtiles);
+    const int c = cc * DW_C + tid;
+    const int r0 = rt * DW_T;
+    const int len = lens ? min(N, __ldg(lens + b)) : N;
+    mbar_wait(&full[s], (it >> 1) & 1);
+    if (c < C) {
+      float w[KS];
 #pragma unroll
-  for (int i = 0; i < KS; ++i) w[i] = __ldg(wt + (size_t)i * C + c);
-  const float bs = __ldg(bias + c);
-  auto ld = [&](int rho) -> float { return (rho >= 0 && rho < len) ? xb[(size_t)rho * C] : 0.f; };
-  float ring[RS];
+      for (int i = 0; i < KS; ++i) w[i] = __ldg(wt + (size_t)i * C + c);
+      const float bs = __ldg(bias + c);
+      const float* xs = buf + (size_t)s * ROWS * DW_C + tid;            // xs[j * DW_C] = x[r0 - HALF + j]
+      float* yb = y + ((size_t)b * N + r0) * C + c;
+      // rows >= len are masked to zero on input (rows outside [0, N) are already zero from the TMA fill)
+      auto ldx = [&](int j) -> float { return (r0 - HALF + j < len) ? xs[(size_t)j * DW_C] : 0.f; };
+      float win[HALO + DW_G];
 #pragma unroll
-  for (int i = 0; i < RS - 1; ++i) ring[i] = ld(r0 - HALF + i);
-  ring[RS - 1] = 0.f;
-  for (int base = r0; base < r1; base += RS) {
+      for (int j = 0; j < HALO; ++j) win[j] = ldx(j);
+#pragma unroll 1
+      for (int g = 0; g < DW_T; g += DW_G) {
+        if (r0 + g >= N) break;
 #pragma unroll
-    for (int u = 0; u < RS; ++u) {
-      const int r = base + u;
-      if (r < r1) {
-        ring[(u + RS - 1) % RS] = ld(r + HALF + PF);      // slot of row r-HALF-1, no longer needed
-        float acc = bs;
+        for (int o = 0; o < DW_G; ++o) win[HALO + o] = ldx(HALO + g + o);
+        float acc[DW_G];
 #pragma unroll
-        for (int i = 0; i < KS; ++i) acc = fmaf(w[i], ring[(u + i) % RS], acc);
-        float out;
-        if (r < len) out = ring[(u + HALF) % RS] + silu(acc);
-        else out = xb[(size_t)r * C];
-        yb[(size_t)r * C] = out;
+        for (int o = 0; o < DW_G; ++o) acc[o] = bs;
+#pragma unroll
+        for (int i = 0; i < KS; ++i)
+#pragma unroll
+          for (int o = 0; o < DW_G; ++o) acc[o] = fmaf(w[i], win[o + i], acc[o]);
+#pragma unroll
+        for (int o = 0; o < DW_G; ++o) {
+          const int r = r0 + g + o;
+          if (r < N) {
+            // the residual uses the UNMASKED x (e2_tts_crossatt3.py:1082: conv(x, mask) + x)
+            const float xc = xs[(size_t)(HALF + g + o) * DW_C];
+            yb[(size_t)(g + o) * C] = (r < len) ? xc + silu(acc[o]) : xc;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < HALO; ++j) win[j] = win[j + DW_G];
       }
     }
+    __syncthreads();     // everyone is done with buffer s before it is refilled two tiles later
   }
 }
 
@@ -310,6 +358,7 @@ extern "C" int e2b_rmsnorm_launch(const float* x, int ldx, void* y, int ldy, con
   const int rows_out = batch * (rows_per_batch - skip_rows);
   if (rows_out <= 0) return 0;
   const int blocks = (rows_out + 7) / 8;
+  ProfScope ps(stream, "rmsnorm", rows_out, C, 0, 3.0 * rows_out * C, (double)rows_out * C * (out_f32 ? 8.0 : 6.0));
   if (out_f32)
     rmsnorm_kernel<true><<<blocks, 256, 0, stream>>>(x, ldx, y, ldy, scale, scale_bstride, rows_out, rows_per_batch, skip_rows, C,
                                                      sqrtf((float)C));
@@ -323,10 +372,25 @@ extern "C" int e2b_dwconv_launch(const float* x, float* y, const float* w, const
                                  int C, int ksize, cudaStream_t stream) {
   if (ksize != 31) { e2b_set_kernel_error("dwconv: kernel size %d unsupported (31 only)", ksize); return -1; }
   if (batch <= 0 || N <= 0) return 0;
-  const int nseg = (N + 95) / 96;
-  const int seg = (N + nseg - 1) / nseg;
-  dim3 grid((C + 127) / 128, nseg, batch);
-  dwconv_kernel<31, 9><<<grid, 128, 0, stream>>>(x, y, w, bias, lens, N, C, seg);
+  if (C % 4) { e2b_set_kernel_error("dwconv: C must be a multiple of 4"); return -1; }
+  CUtensorMap tm;
+  const uint64_t dims[3] = {(uint64_t)C, (uint64_t)N, (uint64_t)batch};
+  const uint64_t strides[2] = {(uint64_t)C * 4, (uint64_t)N * C * 4};
+  const uint32_t box[3] = {DW_C, DW_T + 30, 1};
+  if (make_tmap_generic(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, x, dims, strides, box)) return -1;
+  const int smem = 2 * (DW_T + 30) * DW_C * 4 + 128;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(dwconv_tma_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      e2b_set_kernel_error("dwconv: shared memory attribute failed");
+      return -1;
+    }
+    configured = true;
+  }
+  const int total = batch * ((N + DW_T - 1) / DW_T) * ((C + DW_C - 1) / DW_C);
+  const int grid = total < 2 * 148 ? total : 2 * 148;
+  ProfScope ps(stream, "dwconv", (long long)batch * N, C, ksize, 2.0 * batch * N * (double)C * ksize, 8.0 * batch * N * (double)C);
+  dwconv_tma_kernel<31><<<grid, DW_C, smem, stream>>>(tm, y, w, bias, lens, batch, N, C);
   return check_launch("dwconv");
 }
 
@@ -353,6 +417,7 @@ extern "C" int e2b_init_stream_launch(float* dst, void* dst_b16, const float* re
   const int regs_only = (src_batches < 0);
   const size_t total = (size_t)batch * (regs_only ? R : R + n) * (C / 4);
   if (!total) return 0;
+  ProfScope ps(stream, "init_stream", (long long)batch * (regs_only ? R : R + n), C, 0, 0.0, (double)total * 16.0 * (dst_b16 ? 1.5 : 1.0));
   init_stream_kernel<<<grid_for(total, 256), 256, 0, stream>>>(dst, reinterpret_cast<__nv_bfloat16*>(dst_b16), registers, src,
                                                                src_batches > 0 ? src_batches : 1, drop, add_table, batch, n, R, C,
                                                                regs_only);
@@ -398,6 +463,7 @@ extern "C" int e2b_guided_euler_launch(float* y, const float* pred, int P, int B
     if (check_launch("apg_reduce")) return -1;
   }
   const size_t total4 = pass_stride / 4;
+  ProfScope ps(stream, "guided_euler", P, B, per_sample, 2.0 * P * pass_stride, 4.0 * pass_stride * (P + 2) + 2.0 * pass_stride * n_copies);
   guided_euler_kernel<<<grid_for(total4, 256), 256, 0, stream>>>(y, pred, P, pass_stride, per_sample, total4, gw, dt, apg,
                                                                 keep_parallel, scratch, reinterpret_cast<__nv_bfloat16*>(y_b16), n_copies);
   return check_launch("guided_euler");

@@ -15,6 +15,7 @@
 #include <cstring>
 
 #include "kernels.h"
+#include "prof.h"
 #include "ptx.cuh"
 
 namespace e2b {
@@ -36,136 +37,113 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * 4608 /*epilogue transpose buffers*/ + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;   // 512 or 256: both powers of two
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
-__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&f)[32], int ncols) {
-  if (ncols >= 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-    uint4* p = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u;
-      u.x = pack_bf16(f[8 * i + 0], f[8 * i + 1]);
-      u.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
-      u.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
-      u.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
-      p[i] = u;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < ncols) dst[i] = __float2bfloat16_rn(f[i]);
-  }
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogue.  tcgen05.ld hands every thread one accumulator ROW (32 columns per chunk); writing that layout straight to
+// global memory touches 32 different 128-byte lines per warp instruction (ncu: 32 sectors/request, L1-bound).  Each
+// epilogue warp therefore transposes the 32x32 chunk through a private padded shared-memory buffer, after which lane
+// l owns 4 consecutive columns of row (l / 8) + 4k: a warp-wide 16-byte access now covers 4 rows x 128 contiguous bytes.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int EPI_PITCH4 = 9;                         // float4 per staged row (36 floats: conflict-free 16-byte accesses)
+constexpr int EPI_BUF_BYTES = 32 * EPI_PITCH4 * 16;   // per epilogue warp
+
+struct RowInfo {      // per output row, computed once per tile
+  int row;            // global row (or -1 if out of range)
+  int b, pos;         // batch index / position inside the batch (rows_per_batch or rpb_in based)
+  int orow;           // remapped output row (EPI_F32)
+  bool valid;         // EPI_RESID row mask
+};
+
+__device__ __forceinline__ uint2 pack4_bf16(const float4& v) { return make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)); }
+
+__device__ __forceinline__ float4 ldg4_guard(const float* p, int n) {   // n = valid elements (1..4); p 16-byte aligned iff n == 4
+  if (n >= 4) return __ldg(reinterpret_cast<const float4*>(p));
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  r.x = __ldg(p);
+  if (n > 1) r.y = __ldg(p + 1);
+  if (n > 2) r.z = __ldg(p + 2);
+  return r;
 }
-__device__ __forceinline__ void store_f32x32(float* dst, const float (&f)[32], int ncols) {
-  if (ncols >= 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-    float4* p = reinterpret_cast<float4*>(dst);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) p[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < ncols) dst[i] = f[i];
-  }
+__device__ __forceinline__ void st4_f32(float* p, const float4& v, int n) {
+  if (n >= 4) { *reinterpret_cast<float4*>(p) = v; return; }
+  p[0] = v.x;
+  if (n > 1) p[1] = v.y;
+  if (n > 2) p[2] = v.z;
 }
-__device__ __forceinline__ void load_f32x32(const float* src, float (&f)[32], int ncols) {
-  if (ncols >= 32 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-    const float4* p = reinterpret_cast<const float4*>(src);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 v = p[i];
-      f[4 * i] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
+__device__ __forceinline__ void st4_bf16(__nv_bfloat16* p, const float4& v, int n) {
+  if (n >= 4) { *reinterpret_cast<uint2*>(p) = pack4_bf16(v); return; }
+  p[0] = __float2bfloat16_rn(v.x);
+  if (n > 1) p[1] = __float2bfloat16_rn(v.y);
+  if (n > 2) p[2] = __float2bfloat16_rn(v.z);
+}
+
+// 4 consecutive columns [col, col+4) of one row, n = number of valid columns (1..4).
+//   a    accumulator values (GEGLU: value half, bias already added)      g     GEGLU gate half (bias already added)
+//   pre  per-row operand loaded BEFORE any store of the chunk: residual (RESID), add_table row (F32), rope cos/sin (QKV)
+//   bias4 / gate4  per-column operands shared by all rows of the chunk
+template <int EPI>
+__device__ __forceinline__ void epi4(const e2b_gemm_desc& d, const RowInfo& ri, int col, int n, float4 a, const float4& g, const float4& pre,
+                                     const float4& bias4, const float4& gate4) {
+  if constexpr (EPI == E2B_EPI_BF16) {
+    a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
+    st4_bf16(reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)ri.row * d.ldo + col, a, n);
+  } else if constexpr (EPI == E2B_EPI_F32) {
+    a.x += bias4.x + pre.x; a.y += bias4.y + pre.y; a.z += bias4.z + pre.z; a.w += bias4.w + pre.w;
+    st4_f32(reinterpret_cast<float*>(d.out) + (size_t)ri.orow * d.ldo + col, a, n);
+    if (d.out_b16) st4_bf16(reinterpret_cast<__nv_bfloat16*>(d.out_b16) + (size_t)ri.orow * d.ldo_b16 + col, a, n);
+  } else if constexpr (EPI == E2B_EPI_GEGLU) {
+    a.x *= gelu_erf(g.x); a.y *= gelu_erf(g.y); a.z *= gelu_erf(g.z); a.w *= gelu_erf(g.w);
+    st4_bf16(reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)ri.row * d.ldo + col, a, n);
+  } else if constexpr (EPI == E2B_EPI_RESID) {
+    float4 r = pre;
+    if (ri.valid) {
+      float4 gg = gate4;
+      if (d.gate && d.gate_bstride != 0) gg = ldg4_guard(d.gate + (size_t)ri.b * d.gate_bstride + col, n);
+      r.x += (a.x + bias4.x) * gg.x; r.y += (a.y + bias4.y) * gg.y; r.z += (a.z + bias4.z) * gg.z; r.w += (a.w + bias4.w) * gg.w;
     }
-  } else {
+    st4_f32(reinterpret_cast<float*>(d.out) + (size_t)ri.row * d.ldo + col, r, n);
+    if (d.out_b16) st4_bf16(reinterpret_cast<__nv_bfloat16*>(d.out_b16) + (size_t)ri.row * d.ldo_b16 + col, r, n);
+  } else if constexpr (EPI == E2B_EPI_QKV) {
+    if (col < d.k_end) {
+      // interleaved RoPE (x-transformers rotate_half on adjacent pairs): (x0,x1) -> (x0 c - x1 s, x1 c + x0 s); pre = (c0,s0,c1,s1)
+      const float sc = (col < d.q_end) ? d.q_scale : 1.0f;
+      float4 o;
+      o.x = (a.x * pre.x - a.y * pre.y) * sc;
+      o.y = (a.y * pre.x + a.x * pre.y) * sc;
+      o.z = (a.z * pre.z - a.w * pre.w) * sc;
+      o.w = (a.w * pre.z + a.z * pre.w) * sc;
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)ri.row * d.ldo + col) = pack4_bf16(o);
+    } else {                                       // head-gate columns [v_end, N)
+      const int c = col - d.v_end;
+      const float v[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = (i < ncols) ? src[i] : 0.f;
+      for (int i = 0; i < 4; ++i)
+        if (i < n) d.hgate[(size_t)ri.row * d.hgate_ld + c + i] = sigmoidf_(v[i] + __ldg(d.hgate_bias + c + i));
+    }
   }
 }
 
-// One 32-column chunk of one accumulator row.  `col` = global (packed) column of f[0].
-template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const e2b_gemm_desc& d, int row, int col, float (&f)[32], float (&g)[32]) {
-  const int ncols = min(32, d.N - col);
-  if constexpr (EPI == E2B_EPI_BF16) {
-    if (d.bias) {
+// plain (coherent) 16-byte load: the residual aliases the output buffer, so it must not go through the read-only path
+__device__ __forceinline__ float4 ld4_guard(const float* p, int n) {
+  if (n >= 4) return *reinterpret_cast<const float4*>(p);
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  r.x = p[0];
+  if (n > 1) r.y = p[1];
+  if (n > 2) r.z = p[2];
+  return r;
+}
+
+__device__ __forceinline__ void stage_rows(float4* buf, int lane, const uint32_t (&v)[32]) {
+  float4* w = buf + lane * EPI_PITCH4;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] += (i < ncols) ? __ldg(d.bias + col + i) : 0.f;
-    }
-    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)row * d.ldo + col, f, ncols);
-  } else if constexpr (EPI == E2B_EPI_F32) {
-    const int rin = d.rpb_in > 0 ? row % d.rpb_in : row;
-    const int orow = d.rpb_in > 0 ? (row / d.rpb_in) * d.rpb_out + d.row_off + rin : row;
-    if (d.bias) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] += (i < ncols) ? __ldg(d.bias + col + i) : 0.f;
-    }
-    if (d.add_table) {
-      float t[32];
-      load_f32x32(d.add_table + (size_t)rin * d.ld_add + col, t, ncols);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] += t[i];
-    }
-    store_f32x32(reinterpret_cast<float*>(d.out) + (size_t)orow * d.ldo + col, f, ncols);
-    if (d.out_b16) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(d.out_b16) + (size_t)orow * d.ldo_b16 + col, f, ncols);
-  } else if constexpr (EPI == E2B_EPI_GEGLU) {
-    // f = value columns, g = gate columns of the same packed tile; `col` is the OUTPUT column (inner index)
-    const int nc = min(32, d.N / 2 - col);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = f[i] * gelu_erf(g[i]);
-    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)row * d.ldo + col, f, nc);
-  } else if constexpr (EPI == E2B_EPI_RESID) {
-    const int b = d.rows_per_batch > 0 ? row / d.rows_per_batch : 0;
-    const int pos = d.rows_per_batch > 0 ? row % d.rows_per_batch : row;
-    const bool valid = d.lens ? (pos < __ldg(d.lens + b)) : true;
-    float r[32];
-    load_f32x32(d.resid + (size_t)row * d.ldr + col, r, ncols);
-    if (valid) {
-      if (d.bias) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] += (i < ncols) ? __ldg(d.bias + col + i) : 0.f;
-      }
-      if (d.gate) {
-        const float* gp = d.gate + (size_t)b * d.gate_bstride + col;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] *= (i < ncols) ? __ldg(gp + i) : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) r[i] += f[i];
-    }
-    store_f32x32(reinterpret_cast<float*>(d.out) + (size_t)row * d.ldo + col, r, ncols);
-    if (d.out_b16) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(d.out_b16) + (size_t)row * d.ldo_b16 + col, r, ncols);
-  } else if constexpr (EPI == E2B_EPI_QKV) {
-    const int b = row / d.rows_per_batch;
-    const int pos = row % d.rows_per_batch;
-    if (col < d.k_end) {
-      // interleaved RoPE (x-transformers rotate_half on adjacent pairs): (x0,x1) -> (x0 c - x1 s, x1 c + x0 s)
-      const float sc = (col < d.q_end) ? d.q_scale : 1.0f;
-      const float2* rp = reinterpret_cast<const float2*>(d.rope) + (size_t)(pos + d.pos_off) * 32 + ((col & 63) >> 1);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float2 cs = __ldg(rp + i);
-        const float x0 = f[2 * i], x1 = f[2 * i + 1];
-        f[2 * i] = (x0 * cs.x - x1 * cs.y) * sc;
-        f[2 * i + 1] = (x1 * cs.x + x0 * cs.y) * sc;
-      }
-      store_bf16x32(reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)row * d.ldo + col, f, 32);
-    } else if (col < d.v_end) {
-      const int c = col - d.k_end;
-      const int h = c >> 6, d0 = c & 63;
-      __nv_bfloat16* vp = reinterpret_cast<__nv_bfloat16*>(d.vt) + ((size_t)(b * d.heads_v + h) * 64 + d0) * d.vt_ld + pos;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) vp[(size_t)i * d.vt_ld] = __float2bfloat16_rn(f[i]);
-    } else {
-      const int c = col - d.v_end;
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < ncols) d.hgate[(size_t)row * d.hgate_ld + c + i] = sigmoidf_(f[i] + __ldg(d.hgate_bias + c + i));
-    }
-  }
+  for (int i = 0; i < 8; ++i)
+    w[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
 }
 
 template <int BN, int EPI>
@@ -175,7 +153,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* sEpi = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 4 * EPI_BUF_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::STAGES;
   uint64_t* tfull = bars + 2 * Cfg::STAGES;
@@ -255,49 +234,118 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (TMEM -> registers -> global)
+    // ------------------------------------------------------------ epilogue (TMEM -> regs -> smem transpose -> global)
     const int ew = warp - 4;   // == warp % 4: the TMEM lane quarter this warp may read
+    float4* buf = reinterpret_cast<float4*>(sEpi + ew * EPI_BUF_BYTES);
+    const int rsub = lane >> 3, cg = lane & 7;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-      const int row = m0 + ew * 32 + lane;
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * BN;
+      // rows this lane owns after the transpose: m0 + ew*32 + 4k + rsub
+      RowInfo ri[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int row = m0 + ew * 32 + 4 * k + rsub;
+        ri[k].row = row < d.M ? row : -1;
+        const int rpb = (EPI == E2B_EPI_F32) ? d.rpb_in : d.rows_per_batch;
+        ri[k].b = rpb > 0 ? row / rpb : 0;
+        ri[k].pos = rpb > 0 ? row - ri[k].b * rpb : row;
+        ri[k].orow = (EPI == E2B_EPI_F32 && d.rpb_in > 0) ? ri[k].b * d.rpb_out + d.row_off + ri[k].pos : row;
+        ri[k].valid = (EPI == E2B_EPI_RESID && d.lens && ri[k].row >= 0) ? (ri[k].pos < __ldg(d.lens + ri[k].b)) : true;
+      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       if constexpr (EPI == E2B_EPI_GEGLU) {
         static_assert(BN == 256 || EPI != E2B_EPI_GEGLU, "GEGLU packs 128 value + 128 gate columns per tile");
 #pragma unroll 1
         for (int c = 0; c < BN / 64; ++c) {
-          uint32_t v[32], g[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld32(taddr + BN / 2 + c * 32, g);
+          uint32_t v[32];
+          float4 gt[8];
+          tmem_ld32(taddr + BN / 2 + c * 32, v);     // gate half first
           tmem_ld_wait();
-          float f[32], gg[32];
+          stage_rows(buf, lane, v);
+          __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { f[i] = __uint_as_float(v[i]); gg[i] = __uint_as_float(g[i]); }
-          // packed bias: value bias at packed col, gate bias at packed col + BN/2
+          for (int k = 0; k < 8; ++k) gt[k] = buf[(4 * k + rsub) * EPI_PITCH4 + cg];
+          __syncwarp();
+          tmem_ld32(taddr + c * 32, v);              // value half
+          tmem_ld_wait();
+          stage_rows(buf, lane, v);
+          __syncwarp();
+          const int pc = n0 + c * 32 + cg * 4;       // packed column of the value element; gate is at +BN/2
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
           if (d.bias) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              f[i] += __ldg(d.bias + n0 + c * 32 + i);
-              gg[i] += __ldg(d.bias + n0 + BN / 2 + c * 32 + i);
-            }
+            bv = __ldg(reinterpret_cast<const float4*>(d.bias + pc));
+            bg = __ldg(reinterpret_cast<const float4*>(d.bias + pc + BN / 2));
           }
-          if (row < d.M) epilogue_chunk<EPI>(d, row, n0 / 2 + c * 32, f, gg);
+          const int oc = n0 / 2 + c * 32 + cg * 4;
+          const int n = min(4, d.N / 2 - oc);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float4 a = buf[(4 * k + rsub) * EPI_PITCH4 + cg];
+            a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
+            float4 g = gt[k];
+            g.x += bg.x; g.y += bg.y; g.z += bg.z; g.w += bg.w;
+            if (ri[k].row >= 0 && n > 0) epi4<EPI>(d, ri[k], oc, n, a, g, g, g, g);
+          }
+          __syncwarp();
         }
       } else {
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
-          if (n0 + c * 32 >= d.N) break;
+          const int col0 = n0 + c * 32;
+          if (col0 >= d.N) break;
+          const bool v_chunk = (EPI == E2B_EPI_QKV) && col0 >= d.k_end && col0 < d.v_end;
+          const int col = col0 + cg * 4;
+          const int n = min(4, d.N - col);
+          // per-row / per-column operands first: every global load of the chunk is in flight before the TMEM wait and
+          // before the first store (the output aliases the residual, so the compiler cannot hoist loads over stores)
+          const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 pre[8];
+          float4 bias4 = zero4, gate4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (!v_chunk && n > 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              pre[k] = zero4;
+              if (ri[k].row >= 0) {
+                if constexpr (EPI == E2B_EPI_RESID) pre[k] = ld4_guard(d.resid + (size_t)ri[k].row * d.ldr + col, n);
+                if constexpr (EPI == E2B_EPI_F32) { if (d.add_table) pre[k] = ldg4_guard(d.add_table + (size_t)ri[k].pos * d.ld_add + col, n); }
+                if constexpr (EPI == E2B_EPI_QKV) {
+                  if (col < d.k_end) pre[k] = __ldg(reinterpret_cast<const float4*>(d.rope + ((size_t)(ri[k].pos + d.pos_off) * 32 + ((col & 63) >> 1)) * 2));
+                }
+              }
+            }
+            if (EPI != E2B_EPI_QKV && d.bias) bias4 = ldg4_guard(d.bias + col, n);
+            if (EPI == E2B_EPI_RESID && d.gate && d.gate_bstride == 0) gate4 = ldg4_guard(d.gate + col, n);
+          }
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
-          float f[32];
+          if (v_chunk) {
+            // V^T store: thread = key position, so the 32 lanes of a store are 32 consecutive keys (64 contiguous bytes)
+            const int row = m0 + ew * 32 + lane;
+            if (row < d.M) {
+              const int b = row / d.rows_per_batch, pos = row - b * d.rows_per_batch;
+              const int cc = col0 - d.k_end;
+              __nv_bfloat16* vp = reinterpret_cast<__nv_bfloat16*>(d.vt) + ((size_t)(b * d.heads_v + (cc >> 6)) * 64 + (cc & 63)) * d.vt_ld + pos;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (row < d.M) epilogue_chunk<EPI>(d, row, n0 + c * 32, f, f);
+              for (int i = 0; i < 32; ++i) vp[(size_t)i * d.vt_ld] = __float2bfloat16_rn(__uint_as_float(v[i]));
+            }
+            continue;
+          }
+          stage_rows(buf, lane, v);
+          __syncwarp();
+          if (n > 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4 a = buf[(4 * k + rsub) * EPI_PITCH4 + cg];
+              if (ri[k].row >= 0) epi4<EPI>(d, ri[k], col, n, a, a, pre[k], bias4, gate4);
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -353,6 +401,20 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t col
   return 0;
 }
 
+// generic tiled map (no swizzle): dims/box innermost first, strides in bytes for dims 1..rank-1
+int make_tmap_generic(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims, const uint64_t* strides,
+                      const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { e2b_set_kernel_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; if (i) gs[i - 1] = strides[i - 1]; }
+  CUresult r = enc(m, dt, rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { e2b_set_kernel_error("cuTensorMapEncodeTiled (generic) failed: %d", (int)r); return -1; }
+  return 0;
+}
+
 static int num_sms() {
   static int n = 0;
   if (!n) {
@@ -375,6 +437,11 @@ static int launch_t(const GemmArgs& a, cudaStream_t st) {
   }
   const int tiles = ((a.d.M + BM - 1) / BM) * ((a.d.N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  static const char* kinds[] = {"gemm_bf16", "gemm_f32", "gemm_geglu", "gemm_resid", "gemm_qkv"};
+  const double out_cols = (EPI == E2B_EPI_GEGLU) ? a.d.N / 2.0 : a.d.N;
+  const double out_bytes = (EPI == E2B_EPI_F32) ? 4.0 : (EPI == E2B_EPI_RESID ? 8.0 : 2.0);
+  ProfScope ps(st, kinds[EPI], a.d.M, a.d.N, a.d.K, 2.0 * a.d.M * a.d.N * a.d.K,
+               2.0 * ((double)a.d.M * a.d.K + (double)a.d.N * a.d.K) + out_bytes * a.d.M * out_cols + (a.d.out_b16 ? 2.0 * a.d.M * out_cols : 0.0));
   gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { e2b_set_kernel_error("gemm launch: %s", cudaGetErrorString(e)); return -1; }

@@ -9,6 +9,7 @@
 
 #include "../../include/e2b.h"
 #include "kernels.h"
+#include "prof.h"
 
 namespace e2b {
 
@@ -124,6 +125,7 @@ extern "C" int e2b_melspec_launch(const float* wav, int B, int nw, int n_fft, in
     configured = smem;
   }
   dim3 grid((T + MEL_FR - 1) / MEL_FR, B);
+  ProfScope ps(stream, "melspec", B, nw, n_mels, 0.0, 4.0 * B * ((double)nw + (double)n_mels * T));
   melspec_kernel<<<grid, MEL_THREADS, smem, stream>>>(wav, nw, n_fft, log2n, hop, n_mels, T, window, fb,
                                                       reinterpret_cast<const float2*>(twiddle), out, log_eps);
   cudaError_t e = cudaGetLastError();

@@ -90,6 +90,8 @@ _SIGS = {
     'e2b_guided_euler_launch': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.POINTER(C.c_float),
                                           C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'e2b_kernel_last_error': (C.c_char_p, []),
+    'e2b_prof_enable': (None, [C.c_int]),
+    'e2b_prof_report': (C.c_int, [C.c_char_p, C.c_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
@@ -135,3 +137,15 @@ def int_array(vals):
 def float_array(vals):
     arr = (C.c_float * len(vals))(*[float(v) for v in vals])
     return arr
+
+
+def profile_report():
+    """Per-kernel CUDA-event timings recorded since e2b_prof_enable(1): list of dicts."""
+    n = lib().e2b_prof_report(None, 0)
+    buf = C.create_string_buffer(n + 16)
+    lib().e2b_prof_report(buf, n + 16)
+    rows = []
+    for line in buf.value.decode().splitlines():
+        kind, m, nn, k, cnt, ms, fl, by = line.split()
+        rows.append(dict(kind=kind, m=int(m), n=int(nn), k=int(k), count=int(cnt), ms=float(ms), flops=float(fl), bytes=float(by)))
+    return rows
