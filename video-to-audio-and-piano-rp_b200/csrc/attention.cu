@@ -19,14 +19,17 @@ namespace e2b {
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
-constexpr int ATT_THREADS = 384;           // warps 0-3: TMA / MMA / TMEM alloc / spare ; warps 4-11: softmax + epilogue
+constexpr int ATT_SOFTMAX_WARPS = 16;      // 4 TMEM lane quarters x 4 column quarters of every S tile
+constexpr int ATT_THREADS = 128 + 32 * ATT_SOFTMAX_WARPS;   // warps 0-3: TMA / MMA / TMEM alloc / spare ; then softmax + epilogue
 constexpr int ATT_BQ = 128, ATT_BK = 128, ATT_D = 64;
+constexpr int ATT_KV = 4;                       // K/V ring depth (ncu on the 2-stage version: softmax warps waiting on s_full
+                                                // because the next K tile was only fetched after the PV MMA two tiles back)
 constexpr int ATT_SQ = 0;                       // 16 KB  Q   [128 q, 64 d]
-constexpr int ATT_SK = 16384;                   // 2 x 16 KB  K   [128 keys, 64 d]
-constexpr int ATT_SV = ATT_SK + 2 * 16384;      // 2 x 16 KB  V^T 2 x [64 d, 64 keys]
-constexpr int ATT_SP = ATT_SV + 2 * 16384;      // 2 x 32 KB  P   2 x [128 q, 64 keys]
-constexpr int ATT_LSUM = ATT_SP + 2 * 32768;    // 2 x 128 floats: per-row partial sums of the two column halves
-constexpr int ATT_BAR = ATT_LSUM + 1024;
+constexpr int ATT_SK = 16384;                   // ATT_KV x 16 KB  K   [128 keys, 64 d]
+constexpr int ATT_SV = ATT_SK + ATT_KV * 16384; // ATT_KV x 16 KB  V^T 2 x [64 d, 64 keys]
+constexpr int ATT_SP = ATT_SV + ATT_KV * 16384; // 2 x 32 KB  P   2 x [128 q, 64 keys]
+constexpr int ATT_LSUM = ATT_SP + 2 * 32768;    // 4 x 128 floats: per-row partial sums of the four column quarters
+constexpr int ATT_BAR = ATT_LSUM + 2048;
 constexpr int ATT_SMEM = ATT_BAR + 256 + 1024;
 constexpr uint32_t ATT_TMEM_COLS = 512;         // S0 @0, S1 @128, O @256
 
@@ -49,18 +52,24 @@ struct AttnArgs {
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_constant__ AttnArgs args) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Used directly (no integer round-trip) so the compiler keeps the shared address space: the earlier manual 1024-byte
+  // round-up through uintptr_t turned every access into generic LD.E/ST.E.  SWIZZLE_128B needs a 1024-byte aligned base;
+  // with no static shared memory the dynamic window starts at offset 0 -- checked once below.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) {
+    printf("e2b: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_BAR);
   uint64_t* q_full = bars;          // 1
-  uint64_t* kv_full = bars + 1;     // [2]
-  uint64_t* kv_empty = bars + 3;    // [2]
-  uint64_t* s_full = bars + 5;      // [2]
-  uint64_t* s_empty = bars + 7;     // [2] (256 arrivals)
-  uint64_t* p_full = bars + 9;      // [2] (256 arrivals)
-  uint64_t* p_empty = bars + 11;    // [2]
-  uint64_t* o_full = bars + 13;     // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* o_full = bars + 1;      // 1
+  uint64_t* s_full = bars + 2;      // [2]
+  uint64_t* s_empty = bars + 4;     // [2] (256 arrivals)
+  uint64_t* p_full = bars + 6;      // [2] (256 arrivals)
+  uint64_t* p_empty = bars + 8;     // [2]
+  uint64_t* kv_full = bars + 10;    // [ATT_KV]
+  uint64_t* kv_empty = bars + 10 + ATT_KV;   // [ATT_KV]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * ATT_KV);
 
   const e2b_attn_desc& d = args.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -79,12 +88,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     mbar_init(o_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < ATT_KV; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 256);
-      mbar_init(&p_full[s], 256);
+      mbar_init(&s_empty[s], 32 * ATT_SOFTMAX_WARPS);
+      mbar_init(&p_full[s], 32 * ATT_SOFTMAX_WARPS);
       mbar_init(&p_empty[s], 1);
     }
     fence_mbar_init();
@@ -104,8 +115,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     mbar_arrive_expect_tx(q_full, 16384);
     tma_load_2d(smem + ATT_SQ, &args.tmQ, q_full, d.q_col0 + h * ATT_D, b * d.q_rows_per_batch + qt * ATT_BQ);
     for (int j = 0; j < nt; ++j) {
-      const int s = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
+      const int s = j % ATT_KV;
+      const uint32_t ph = (j / ATT_KV) & 1;
       mbar_wait(&kv_empty[s], ph ^ 1);
       mbar_arrive_expect_tx(&kv_full[s], 32768);
       tma_load_2d(smem + ATT_SK + s * 16384, &args.tmK, &kv_full[s], d.k_col0 + h * ATT_D, kvb * d.kv_rows_per_batch + j * ATT_BK);
@@ -119,12 +130,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, ATT_D);
     const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SQ));
     auto issue_s = [&](int j) {
-      const int s = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
-      mbar_wait(&kv_full[s], ph);
-      mbar_wait(&s_empty[s], ph ^ 1);
+      const int s = j & 1, ks = j % ATT_KV;
+      mbar_wait(&kv_full[ks], (j / ATT_KV) & 1);
+      mbar_wait(&s_empty[s], ((j >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SK + s * 16384));
+      const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SK + ks * 16384));
 #pragma unroll
       for (int k = 0; k < ATT_D / 16; ++k)
         umma_bf16_ss(tmem_base + s * ATT_BK, dq + k * UMMA_K_STEP_ENC, dk + k * UMMA_K_STEP_ENC, idesc_s, k != 0 ? 1u : 0u);
@@ -142,26 +152,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       for (int kk = 0; kk < ATT_BK / 16; ++kk) {
         const int atom = kk >> 2, k4 = kk & 3;
         const uint64_t dp = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SP + s * 32768 + atom * 16384)) + k4 * UMMA_K_STEP_ENC;
-        const uint64_t dv = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SV + s * 16384 + atom * 8192)) + k4 * UMMA_K_STEP_ENC;
+        const uint64_t dv = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SV + (j % ATT_KV) * 16384 + atom * 8192)) + k4 * UMMA_K_STEP_ENC;
         umma_bf16_ss(tmem_o, dp, dv, idesc_o, (j | kk) != 0 ? 1u : 0u);
       }
-      umma_commit(&kv_empty[s]);
+      umma_commit(&kv_empty[j % ATT_KV]);
       umma_commit(&p_empty[s]);
     }
     umma_commit(o_full);
   } else if (warp >= 4) {
     // ------------------------------------------------------------ softmax + epilogue
-    // 8 warps: warp (4 + q) and (8 + q) both own TMEM lane quarter q (= query rows 32q..32q+31); the first group handles
-    // key columns 0-63 of every S tile, the second 64-127 (ncu on the 4-warp version: issue-limited, 12 % warps active).
+    // 16 warps: warp (4 + 4c + q) owns TMEM lane quarter q (query rows 32q..32q+31) and key columns 32c..32c+31 of every
+    // S tile.  (ncu on the 4- and 8-warp versions: IPC per scheduler ~0.3, nothing saturated -- latency bound, so the
+    // fix is more warps per scheduler, not fewer instructions.)
     const int sw = warp - 4;
-    const int quarter = sw & 3, half = sw >> 2;
+    const int quarter = sw & 3, cq = sw >> 2;
     const int r = quarter * 32 + lane;                  // row inside the tile == TMEM lane
     const int q_pos = qt * ATT_BQ + r;
     const bool q_valid = q_pos < d.q_rows_per_batch;
     const bool warp_valid = (qt * ATT_BQ + quarter * 32) < d.q_rows_per_batch;
     const uint32_t lane_base = uint32_t(quarter * 32) << 16;
     const ClampPoly cp = args.cp;
-    const uint32_t p_row_off = (r >> 3) * 1024 + (r & 7) * 128;
+    const int c0 = cq * 32;                             // first key column of this warp inside the tile
+    // P: keys c0..c0+31 live in swizzle atom (cq >> 1), 16-byte chunks ((cq & 1) * 4 + q) ^ (r & 7) of the 128-byte row
+    const uint32_t p_off = (cq >> 1) * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
     float l0 = 0.f, l1 = 0.f;
 
     for (int j = 0; j < nt; ++j) {
@@ -171,19 +184,19 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       mbar_wait(&s_full[s], ph);
       tc_fence_after();
       mbar_wait(&p_empty[s], ph ^ 1);
-      uint8_t* atom = smem + ATT_SP + s * 32768 + half * 16384 + p_row_off;      // keys 64*half .. +63 of this row
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c0 = half * 64 + cc * 32;             // first key column of this chunk inside the tile
-        uint32_t pk[16];
-        if (warp_valid && c0 < nvalid) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + lane_base + s * ATT_BK + c0, v);
+      uint8_t* prow = smem + ATT_SP + s * 32768 + p_off;
+      const bool live = warp_valid && c0 < nvalid;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {                  // two 16-column halves keep the register footprint small
+        uint32_t pk[8];
+        if (live) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + lane_base + s * ATT_BK + c0 + hh * 16, v);
           tmem_ld_wait();
-          float arg[32];
+          float arg[16];
           float wm = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 16; ++i) {
             const float z = __uint_as_float(v[i]);
             const float w = z * z;
             wm = fmaxf(wm, w);
@@ -195,33 +208,32 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
           }
           if (__any_sync(0xffffffffu, wm >= cp.wmax)) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 16; ++i) {
               const float z = __uint_as_float(v[i]);
               if (z * z >= cp.wmax) arg[i] = softclamp_exp2_arg_exact(z, cp.clamp);
             }
           }
-          float p[32];
+          float p[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) p[i] = ex2_approx(arg[i]);
+          for (int i = 0; i < 16; ++i) p[i] = ex2_approx(arg[i]);
           if (c0 + 32 > nvalid) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) p[i] = (c0 + i < nvalid) ? p[i] : 0.f;
+            for (int i = 0; i < 16; ++i) p[i] = (c0 + hh * 16 + i < nvalid) ? p[i] : 0.f;
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 8; ++i) {
             l0 += p[2 * i];
             l1 += p[2 * i + 1];
             pk[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          for (int i = 0; i < 8; ++i) pk[i] = 0u;
         }
-        // 16-byte chunks (cc*4 + q) of the 128-byte swizzled row
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = (cc * 4 + q) ^ (r & 7);
-          *reinterpret_cast<uint4*>(atom + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        for (int q = 0; q < 2; ++q) {
+          const int chunk = ((cq & 1) * 4 + hh * 2 + q) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
       }
       tc_fence_before();
@@ -230,11 +242,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       mbar_arrive(&p_full[s]);
     }
 
-    // combine the two column halves' row sums
+    // combine the four column quarters' row sums
     float* lsum = reinterpret_cast<float*>(smem + ATT_LSUM);
-    lsum[half * 128 + r] = l0 + l1;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float l = lsum[r] + lsum[128 + r];
+    lsum[cq * 128 + r] = l0 + l1;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * ATT_SOFTMAX_WARPS) : "memory");
+    const float l = (lsum[r] + lsum[128 + r]) + (lsum[256 + r] + lsum[384 + r]);
 
     mbar_wait(o_full, 0);
     tc_fence_after();
@@ -243,15 +255,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       scale = 1.0f / l;
       if (d.hgate) scale *= __ldg(d.hgate + (size_t)(b * d.q_rows_per_batch + q_pos) * d.hgate_ld + h);
     }
-    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)(b * d.q_rows_per_batch + q_pos) * d.ldo + h * ATT_D + half * 32;
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)(b * d.q_rows_per_batch + q_pos) * d.ldo + h * ATT_D + cq * 16;
     {
-      uint32_t v[32];
-      tmem_ld32(tmem_o + lane_base + half * 32, v);
+      uint32_t v[16];
+      tmem_ld16(tmem_o + lane_base + cq * 16, v);
       tmem_ld_wait();
       if (q_valid) {
         uint4* o4 = reinterpret_cast<uint4*>(op);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
           uint4 u;
           u.x = pack_bf16(__uint_as_float(v[8 * i + 0]) * scale, __uint_as_float(v[8 * i + 1]) * scale);
           u.y = pack_bf16(__uint_as_float(v[8 * i + 2]) * scale, __uint_as_float(v[8 * i + 3]) * scale);

@@ -78,17 +78,19 @@ int make_tmap_generic(CUtensorMap* m, CUtensorMapDataType dt, int rank, const vo
                       const uint32_t* box);
 
 template <int KS>
-__global__ void __launch_bounds__(DW_C) dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmx, float* __restrict__ y,
+__global__ void __launch_bounds__(2 * DW_C, 2) dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmx, float* __restrict__ y,
                                                           const float* __restrict__ wt, const float* __restrict__ bias,
                                                           const int* __restrict__ lens, int batch, int N, int C) {
   constexpr int HALO = KS - 1, HALF = KS / 2, ROWS = DW_T + HALO;
-  extern __shared__ uint8_t smem_raw[];
-  float* buf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));   // 2 x [ROWS][DW_C]
-  __shared__ uint64_t full[2];
-  const int tid = threadIdx.x;
+  // no static shared memory: the dynamic window starts at offset 0 (128-byte alignment needed by the TMA destination) and
+  // is used directly so loads stay LDS (a uintptr_t round-trip would make them generic LD.E)
+  extern __shared__ __align__(128) float buf[];               // 2 x [ROWS][DW_C], then two mbarriers
+  uint64_t* full = reinterpret_cast<uint64_t*>(buf + 2 * ROWS * DW_C);
+  const int tid = threadIdx.x & (DW_C - 1);       // channel inside the tile
+  const int rhalf = threadIdx.x / DW_C;           // which 32-row half of the tile this thread produces
   const int cchunks = (C + DW_C - 1) / DW_C, rtiles = (N + DW_T - 1) / DW_T;
   const int total = batch * rtiles * cchunks;
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
     fence_mbar_init();
@@ -100,12 +102,12 @@ __global__ void __launch_bounds__(DW_C) dwconv_tma_kernel(const __grid_constant_
     mbar_arrive_expect_tx(&full[s], ROWS * DW_C * 4);
     tma_load_3d(buf + (size_t)s * ROWS * DW_C, &tmx, &full[s], cc * DW_C, rt * DW_T - HALF, b);
   };
-  if (tid == 0 && (int)blockIdx.x < total) issue(blockIdx.x, 0);
+  if (threadIdx.x == 0 && (int)blockIdx.x < total) issue(blockIdx.x, 0);
 
   int it = 0;
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
     const int s = it & 1;
-    if (tid == 0 && tile + (int)gridDim.x < total) issue(tile + gridDim.x, s ^ 1);
+    if (threadIdx.x == 0 && tile + (int)gridDim.x < total) issue(tile + gridDim.x, s ^ 1);
     const int cc = tile % cchunks, rt = (tile / cchunks) % rtiles, b = tile / (cchunks * rtiles);
     const int c = cc * DW_C + tid;
     const int r0 = rt * DW_T;
@@ -121,10 +123,11 @@ __global__ void __launch_bounds__(DW_C) dwconv_tma_kernel(const __grid_constant_
       // rows >= len are masked to zero on input (rows outside [0, N) are already zero from the TMA fill)
       auto ldx = [&](int j) -> float { return (r0 - HALF + j < len) ? xs[(size_t)j * DW_C] : 0.f; };
       float win[HALO + DW_G];
+      const int g0 = rhalf * (DW_T / 2);
 #pragma unroll
-      for (int j = 0; j < HALO; ++j) win[j] = ldx(j);
+      for (int j = 0; j < HALO; ++j) win[j] = ldx(g0 + j);
 #pragma unroll 1
-      for (int g = 0; g < DW_T; g += DW_G) {
+      for (int g = g0; g < g0 + DW_T / 2; g += DW_G) {
         if (r0 + g >= N) break;
 #pragma unroll
         for (int o = 0; o < DW_G; ++o) win[HALO + o] = ldx(HALO + g + o);
@@ -378,7 +381,7 @@ extern "C" int e2b_dwconv_launch(const float* x, float* y, const float* w, const
   const uint64_t strides[2] = {(uint64_t)C * 4, (uint64_t)N * C * 4};
   const uint32_t box[3] = {DW_C, DW_T + 30, 1};
   if (make_tmap_generic(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, x, dims, strides, box)) return -1;
-  const int smem = 2 * (DW_T + 30) * DW_C * 4 + 128;
+  const int smem = 2 * (DW_T + 30) * DW_C * 4 + 16;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(dwconv_tma_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
@@ -390,7 +393,7 @@ extern "C" int e2b_dwconv_launch(const float* x, float* y, const float* w, const
   const int total = batch * ((N + DW_T - 1) / DW_T) * ((C + DW_C - 1) / DW_C);
   const int grid = total < 2 * 148 ? total : 2 * 148;
   ProfScope ps(stream, "dwconv", (long long)batch * N, C, ksize, 2.0 * batch * N * (double)C * ksize, 8.0 * batch * N * (double)C);
-  dwconv_tma_kernel<31><<<grid, DW_C, smem, stream>>>(tm, y, w, bias, lens, batch, N, C);
+  dwconv_tma_kernel<31><<<grid, 2 * DW_C, smem, stream>>>(tm, y, w, bias, lens, batch, N, C);
   return check_launch("dwconv");
 }
 

@@ -48,96 +48,17 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 // Epilogue.  tcgen05.ld hands every thread one accumulator ROW (32 columns per chunk); writing that layout straight to
 // global memory touches 32 different 128-byte lines per warp instruction (ncu: 32 sectors/request, L1-bound).  Each
 // epilogue warp therefore transposes the 32x32 chunk through a private padded shared-memory buffer, after which lane
-// l owns 4 consecutive columns of row (l / 8) + 4k: a warp-wide 16-byte access now covers 4 rows x 128 contiguous bytes.
+// l owns 4 consecutive columns (cg = l % 8) of rows (l / 8) + 4k, k = 0..7: a warp-wide 16-byte access covers
+// 4 rows x 128 contiguous bytes.  The per-row loop is kept branch-free and address-light: row base pointers are computed
+// once per tile, operand presence is tested once per chunk (ncu on the first "guarded" version: 15 branches and 17
+// integer ops per store -- instruction bound).  All column counts must be multiples of 4 (checked on the host).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int EPI_PITCH4 = 9;                         // float4 per staged row (36 floats: conflict-free 16-byte accesses)
 constexpr int EPI_BUF_BYTES = 32 * EPI_PITCH4 * 16;   // per epilogue warp
 
-struct RowInfo {      // per output row, computed once per tile
-  int row;            // global row (or -1 if out of range)
-  int b, pos;         // batch index / position inside the batch (rows_per_batch or rpb_in based)
-  int orow;           // remapped output row (EPI_F32)
-  bool valid;         // EPI_RESID row mask
-};
-
 __device__ __forceinline__ uint2 pack4_bf16(const float4& v) { return make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)); }
-
-__device__ __forceinline__ float4 ldg4_guard(const float* p, int n) {   // n = valid elements (1..4); p 16-byte aligned iff n == 4
-  if (n >= 4) return __ldg(reinterpret_cast<const float4*>(p));
-  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-  r.x = __ldg(p);
-  if (n > 1) r.y = __ldg(p + 1);
-  if (n > 2) r.z = __ldg(p + 2);
-  return r;
-}
-__device__ __forceinline__ void st4_f32(float* p, const float4& v, int n) {
-  if (n >= 4) { *reinterpret_cast<float4*>(p) = v; return; }
-  p[0] = v.x;
-  if (n > 1) p[1] = v.y;
-  if (n > 2) p[2] = v.z;
-}
-__device__ __forceinline__ void st4_bf16(__nv_bfloat16* p, const float4& v, int n) {
-  if (n >= 4) { *reinterpret_cast<uint2*>(p) = pack4_bf16(v); return; }
-  p[0] = __float2bfloat16_rn(v.x);
-  if (n > 1) p[1] = __float2bfloat16_rn(v.y);
-  if (n > 2) p[2] = __float2bfloat16_rn(v.z);
-}
-
-// 4 consecutive columns [col, col+4) of one row, n = number of valid columns (1..4).
-//   a    accumulator values (GEGLU: value half, bias already added)      g     GEGLU gate half (bias already added)
-//   pre  per-row operand loaded BEFORE any store of the chunk: residual (RESID), add_table row (F32), rope cos/sin (QKV)
-//   bias4 / gate4  per-column operands shared by all rows of the chunk
-template <int EPI>
-__device__ __forceinline__ void epi4(const e2b_gemm_desc& d, const RowInfo& ri, int col, int n, float4 a, const float4& g, const float4& pre,
-                                     const float4& bias4, const float4& gate4) {
-  if constexpr (EPI == E2B_EPI_BF16) {
-    a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
-    st4_bf16(reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)ri.row * d.ldo + col, a, n);
-  } else if constexpr (EPI == E2B_EPI_F32) {
-    a.x += bias4.x + pre.x; a.y += bias4.y + pre.y; a.z += bias4.z + pre.z; a.w += bias4.w + pre.w;
-    st4_f32(reinterpret_cast<float*>(d.out) + (size_t)ri.orow * d.ldo + col, a, n);
-    if (d.out_b16) st4_bf16(reinterpret_cast<__nv_bfloat16*>(d.out_b16) + (size_t)ri.orow * d.ldo_b16 + col, a, n);
-  } else if constexpr (EPI == E2B_EPI_GEGLU) {
-    a.x *= gelu_erf(g.x); a.y *= gelu_erf(g.y); a.z *= gelu_erf(g.z); a.w *= gelu_erf(g.w);
-    st4_bf16(reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)ri.row * d.ldo + col, a, n);
-  } else if constexpr (EPI == E2B_EPI_RESID) {
-    float4 r = pre;
-    if (ri.valid) {
-      float4 gg = gate4;
-      if (d.gate && d.gate_bstride != 0) gg = ldg4_guard(d.gate + (size_t)ri.b * d.gate_bstride + col, n);
-      r.x += (a.x + bias4.x) * gg.x; r.y += (a.y + bias4.y) * gg.y; r.z += (a.z + bias4.z) * gg.z; r.w += (a.w + bias4.w) * gg.w;
-    }
-    st4_f32(reinterpret_cast<float*>(d.out) + (size_t)ri.row * d.ldo + col, r, n);
-    if (d.out_b16) st4_bf16(reinterpret_cast<__nv_bfloat16*>(d.out_b16) + (size_t)ri.row * d.ldo_b16 + col, r, n);
-  } else if constexpr (EPI == E2B_EPI_QKV) {
-    if (col < d.k_end) {
-      // interleaved RoPE (x-transformers rotate_half on adjacent pairs): (x0,x1) -> (x0 c - x1 s, x1 c + x0 s); pre = (c0,s0,c1,s1)
-      const float sc = (col < d.q_end) ? d.q_scale : 1.0f;
-      float4 o;
-      o.x = (a.x * pre.x - a.y * pre.y) * sc;
-      o.y = (a.y * pre.x + a.x * pre.y) * sc;
-      o.z = (a.z * pre.z - a.w * pre.w) * sc;
-      o.w = (a.w * pre.z + a.z * pre.w) * sc;
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)ri.row * d.ldo + col) = pack4_bf16(o);
-    } else {                                       // head-gate columns [v_end, N)
-      const int c = col - d.v_end;
-      const float v[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (i < n) d.hgate[(size_t)ri.row * d.hgate_ld + c + i] = sigmoidf_(v[i] + __ldg(d.hgate_bias + c + i));
-    }
-  }
-}
-
-// plain (coherent) 16-byte load: the residual aliases the output buffer, so it must not go through the read-only path
-__device__ __forceinline__ float4 ld4_guard(const float* p, int n) {
-  if (n >= 4) return *reinterpret_cast<const float4*>(p);
-  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-  r.x = p[0];
-  if (n > 1) r.y = p[1];
-  if (n > 2) r.z = p[2];
-  return r;
-}
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4_one() { return make_float4(1.f, 1.f, 1.f, 1.f); }
 
 __device__ __forceinline__ void stage_rows(float4* buf, int lane, const uint32_t (&v)[32]) {
   float4* w = buf + lane * EPI_PITCH4;
@@ -146,11 +67,26 @@ __device__ __forceinline__ void stage_rows(float4* buf, int lane, const uint32_t
     w[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
 }
 
+// Row base pointers of the 8 rows a lane owns after the transpose (byte pointers; out == nullptr <=> row >= M).
+struct EpiRows {
+  char* out[8];          // primary output row (bf16 or fp32)
+  char* out2[8];         // EPI_F32 / EPI_RESID: bf16 copy row (or nullptr) ; EPI_QKV: head-gate row (fp32)
+  const char* aux[8];    // EPI_RESID: residual row ; EPI_F32: add_table row (or nullptr) ; EPI_QKV: rope row of this position
+  const char* gate[8];   // EPI_RESID with a per-batch gate: gate row of this row's batch item
+  bool valid[8];         // EPI_RESID row mask (valid length)
+};
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmArgs args) {
   using Cfg = GemmCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Used directly (no integer round-trip) so the compiler keeps the shared address space: the earlier manual 1024-byte
+  // round-up through uintptr_t turned every access into generic LD.E/ST.E.  SWIZZLE_128B needs a 1024-byte aligned base;
+  // with no static shared memory the dynamic window starts at offset 0 -- checked once below.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) {
+    printf("e2b: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
   uint8_t* sEpi = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -238,26 +174,52 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     const int ew = warp - 4;   // == warp % 4: the TMEM lane quarter this warp may read
     float4* buf = reinterpret_cast<float4*>(sEpi + ew * EPI_BUF_BYTES);
     const int rsub = lane >> 3, cg = lane & 7;
+    const float4* bufr = buf + rsub * EPI_PITCH4 + cg;          // + 4k * EPI_PITCH4 selects row 4k + rsub
+    const bool per_batch_gate = (EPI == E2B_EPI_RESID) && d.gate && d.gate_bstride != 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * BN;
-      // rows this lane owns after the transpose: m0 + ew*32 + 4k + rsub
-      RowInfo ri[8];
+      const int ncols = min(BN, d.N - n0);                      // valid packed columns of this tile (multiple of 4)
+      EpiRows R;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int row = m0 + ew * 32 + 4 * k + rsub;
-        ri[k].row = row < d.M ? row : -1;
-        const int rpb = (EPI == E2B_EPI_F32) ? d.rpb_in : d.rows_per_batch;
-        ri[k].b = rpb > 0 ? row / rpb : 0;
-        ri[k].pos = rpb > 0 ? row - ri[k].b * rpb : row;
-        ri[k].orow = (EPI == E2B_EPI_F32 && d.rpb_in > 0) ? ri[k].b * d.rpb_out + d.row_off + ri[k].pos : row;
-        ri[k].valid = (EPI == E2B_EPI_RESID && d.lens && ri[k].row >= 0) ? (ri[k].pos < __ldg(d.lens + ri[k].b)) : true;
+        const bool ok = row < d.M;
+        R.out[k] = nullptr; R.out2[k] = nullptr; R.aux[k] = nullptr; R.gate[k] = nullptr; R.valid[k] = true;
+        if (ok) {
+          if constexpr (EPI == E2B_EPI_BF16) {
+            R.out[k] = reinterpret_cast<char*>(reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)row * d.ldo + n0);
+          } else if constexpr (EPI == E2B_EPI_GEGLU) {
+            R.out[k] = reinterpret_cast<char*>(reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)row * d.ldo + n0 / 2);
+          } else if constexpr (EPI == E2B_EPI_F32) {
+            int orow = row, pos = row;
+            if (d.rpb_in > 0) { const int b = row / d.rpb_in; pos = row - b * d.rpb_in; orow = b * d.rpb_out + d.row_off + pos; }
+            R.out[k] = reinterpret_cast<char*>(reinterpret_cast<float*>(d.out) + (size_t)orow * d.ldo + n0);
+            if (d.out_b16) R.out2[k] = reinterpret_cast<char*>(reinterpret_cast<__nv_bfloat16*>(d.out_b16) + (size_t)orow * d.ldo_b16 + n0);
+            if (d.add_table) R.aux[k] = reinterpret_cast<const char*>(d.add_table + (size_t)pos * d.ld_add + n0);
+          } else if constexpr (EPI == E2B_EPI_RESID) {
+            R.out[k] = reinterpret_cast<char*>(reinterpret_cast<float*>(d.out) + (size_t)row * d.ldo + n0);
+            R.aux[k] = reinterpret_cast<const char*>(d.resid + (size_t)row * d.ldr + n0);
+            if (d.out_b16) R.out2[k] = reinterpret_cast<char*>(reinterpret_cast<__nv_bfloat16*>(d.out_b16) + (size_t)row * d.ldo_b16 + n0);
+            if (d.rows_per_batch > 0) {
+              const int b = row / d.rows_per_batch, pos = row - b * d.rows_per_batch;
+              if (d.lens) R.valid[k] = pos < __ldg(d.lens + b);
+              if (per_batch_gate) R.gate[k] = reinterpret_cast<const char*>(d.gate + (size_t)b * d.gate_bstride + n0);
+            }
+          } else if constexpr (EPI == E2B_EPI_QKV) {
+            const int b = row / d.rows_per_batch, pos = row - b * d.rows_per_batch;
+            R.out[k] = reinterpret_cast<char*>(reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)row * d.ldo);
+            R.aux[k] = reinterpret_cast<const char*>(d.rope + (size_t)(pos + d.pos_off) * 64);
+            R.out2[k] = reinterpret_cast<char*>(d.hgate + (size_t)row * d.hgate_ld);
+          }
+        }
       }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
+
       if constexpr (EPI == E2B_EPI_GEGLU) {
         static_assert(BN == 256 || EPI != E2B_EPI_GEGLU, "GEGLU packs 128 value + 128 gate columns per tile");
 #pragma unroll 1
@@ -269,62 +231,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
           stage_rows(buf, lane, v);
           __syncwarp();
 #pragma unroll
-          for (int k = 0; k < 8; ++k) gt[k] = buf[(4 * k + rsub) * EPI_PITCH4 + cg];
+          for (int k = 0; k < 8; ++k) gt[k] = bufr[4 * k * EPI_PITCH4];
           __syncwarp();
           tmem_ld32(taddr + c * 32, v);              // value half
           tmem_ld_wait();
           stage_rows(buf, lane, v);
           __syncwarp();
-          const int pc = n0 + c * 32 + cg * 4;       // packed column of the value element; gate is at +BN/2
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
+          const int pc = n0 + c * 32 + cg * 4;       // packed column of the value element; its gate is at +BN/2
+          float4 bv = f4_zero(), bg = f4_zero();
           if (d.bias) {
             bv = __ldg(reinterpret_cast<const float4*>(d.bias + pc));
             bg = __ldg(reinterpret_cast<const float4*>(d.bias + pc + BN / 2));
           }
-          const int oc = n0 / 2 + c * 32 + cg * 4;
-          const int n = min(4, d.N / 2 - oc);
+          const int ob = (c * 32 + cg * 4) * 2;      // byte offset inside the tile's bf16 output row
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            float4 a = buf[(4 * k + rsub) * EPI_PITCH4 + cg];
-            a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
-            float4 g = gt[k];
-            g.x += bg.x; g.y += bg.y; g.z += bg.z; g.w += bg.w;
-            if (ri[k].row >= 0 && n > 0) epi4<EPI>(d, ri[k], oc, n, a, g, g, g, g);
+            const float4 a = bufr[4 * k * EPI_PITCH4];
+            float4 o;
+            o.x = (a.x + bv.x) * gelu_erf(gt[k].x + bg.x);
+            o.y = (a.y + bv.y) * gelu_erf(gt[k].y + bg.y);
+            o.z = (a.z + bv.z) * gelu_erf(gt[k].z + bg.z);
+            o.w = (a.w + bv.w) * gelu_erf(gt[k].w + bg.w);
+            if (R.out[k]) *reinterpret_cast<uint2*>(R.out[k] + ob) = pack4_bf16(o);
           }
           __syncwarp();
         }
-      } else {
+      } else if constexpr (EPI == E2B_EPI_QKV) {
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           const int col0 = n0 + c * 32;
           if (col0 >= d.N) break;
-          const bool v_chunk = (EPI == E2B_EPI_QKV) && col0 >= d.k_end && col0 < d.v_end;
           const int col = col0 + cg * 4;
-          const int n = min(4, d.N - col);
-          // per-row / per-column operands first: every global load of the chunk is in flight before the TMEM wait and
-          // before the first store (the output aliases the residual, so the compiler cannot hoist loads over stores)
-          const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 pre[8];
-          float4 bias4 = zero4, gate4 = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (!v_chunk && n > 0) {
+          float4 cs[8];
+          if (col0 < d.k_end) {                      // rope (cos, sin) pairs of this lane's two column pairs, all 8 rows
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              pre[k] = zero4;
-              if (ri[k].row >= 0) {
-                if constexpr (EPI == E2B_EPI_RESID) pre[k] = ld4_guard(d.resid + (size_t)ri[k].row * d.ldr + col, n);
-                if constexpr (EPI == E2B_EPI_F32) { if (d.add_table) pre[k] = ldg4_guard(d.add_table + (size_t)ri[k].pos * d.ld_add + col, n); }
-                if constexpr (EPI == E2B_EPI_QKV) {
-                  if (col < d.k_end) pre[k] = __ldg(reinterpret_cast<const float4*>(d.rope + ((size_t)(ri[k].pos + d.pos_off) * 32 + ((col & 63) >> 1)) * 2));
-                }
-              }
-            }
-            if (EPI != E2B_EPI_QKV && d.bias) bias4 = ldg4_guard(d.bias + col, n);
-            if (EPI == E2B_EPI_RESID && d.gate && d.gate_bstride == 0) gate4 = ldg4_guard(d.gate + col, n);
+            for (int k = 0; k < 8; ++k)
+              cs[k] = R.aux[k] ? __ldg(reinterpret_cast<const float4*>(R.aux[k] + ((col & 63) >> 1) * 8)) : f4_zero();
           }
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
-          if (v_chunk) {
+          if (col0 >= d.k_end && col0 < d.v_end) {
             // V^T store: thread = key position, so the 32 lanes of a store are 32 consecutive keys (64 contiguous bytes)
             const int row = m0 + ew * 32 + lane;
             if (row < d.M) {
@@ -338,14 +285,107 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
           }
           stage_rows(buf, lane, v);
           __syncwarp();
-          if (n > 0) {
+          if (col0 < d.k_end) {
+            // interleaved RoPE (x-transformers rotate_half on adjacent pairs): (x0,x1) -> (x0 c - x1 s, x1 c + x0 s)
+            const float sc = (col0 < d.q_end) ? d.q_scale : 1.0f;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              const float4 a = buf[(4 * k + rsub) * EPI_PITCH4 + cg];
-              if (ri[k].row >= 0) epi4<EPI>(d, ri[k], col, n, a, a, pre[k], bias4, gate4);
+              const float4 a = bufr[4 * k * EPI_PITCH4];
+              float4 o;
+              o.x = (a.x * cs[k].x - a.y * cs[k].y) * sc;
+              o.y = (a.y * cs[k].x + a.x * cs[k].y) * sc;
+              o.z = (a.z * cs[k].z - a.w * cs[k].w) * sc;
+              o.w = (a.w * cs[k].z + a.z * cs[k].w) * sc;
+              if (R.out[k]) *reinterpret_cast<uint2*>(R.out[k] + col * 2) = pack4_bf16(o);
+            }
+          } else if (col < d.N) {                    // head-gate columns [v_end, N): few, scalar stores
+            const int gc = col - d.v_end;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4 a = bufr[4 * k * EPI_PITCH4];
+              const float e[4] = {a.x, a.y, a.z, a.w};
+              if (R.out2[k]) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (col + i < d.N) reinterpret_cast<float*>(R.out2[k])[gc + i] = sigmoidf_(e[i] + __ldg(d.hgate_bias + gc + i));
+              }
             }
           }
           __syncwarp();
+        }
+      } else {
+        // BF16 / F32 / RESID: per-row operand sets A and B are loaded one chunk ahead and used alternately
+        auto load_ops = [&](int c, float4 (&pre)[8], float4& bias4, float4& gate4) {
+          const int lc = c * 32 + cg * 4;                         // column inside the tile
+          bias4 = f4_zero();
+          gate4 = f4_one();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) pre[k] = f4_zero();
+          if (lc >= ncols) return;
+          if constexpr (EPI == E2B_EPI_RESID) {
+            // plain (coherent) loads: the residual aliases the output buffer
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (R.aux[k]) pre[k] = *reinterpret_cast<const float4*>(R.aux[k] + lc * 4);
+            if (d.gate && !per_batch_gate) gate4 = __ldg(reinterpret_cast<const float4*>(d.gate + n0 + lc));
+          }
+          if constexpr (EPI == E2B_EPI_F32) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (R.aux[k]) pre[k] = __ldg(reinterpret_cast<const float4*>(R.aux[k] + lc * 4));
+          }
+          if (d.bias) bias4 = __ldg(reinterpret_cast<const float4*>(d.bias + n0 + lc));
+        };
+        auto process = [&](int c, const float4 (&pre)[8], const float4& bias4, const float4& gate4) {
+          const int lc = c * 32 + cg * 4;
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          stage_rows(buf, lane, v);
+          __syncwarp();
+          if (lc < ncols) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4 a = bufr[4 * k * EPI_PITCH4];
+              if constexpr (EPI == E2B_EPI_BF16) {
+                const float4 o = make_float4(a.x + bias4.x, a.y + bias4.y, a.z + bias4.z, a.w + bias4.w);
+                if (R.out[k]) *reinterpret_cast<uint2*>(R.out[k] + lc * 2) = pack4_bf16(o);
+              } else if constexpr (EPI == E2B_EPI_F32) {
+                const float4 o = make_float4(a.x + bias4.x + pre[k].x, a.y + bias4.y + pre[k].y, a.z + bias4.z + pre[k].z, a.w + bias4.w + pre[k].w);
+                if (R.out[k]) {
+                  *reinterpret_cast<float4*>(R.out[k] + lc * 4) = o;
+                  if (R.out2[k]) *reinterpret_cast<uint2*>(R.out2[k] + lc * 2) = pack4_bf16(o);
+                }
+              } else {   // RESID
+                float4 gg = gate4;
+                if (per_batch_gate && R.gate[k]) gg = __ldg(reinterpret_cast<const float4*>(R.gate[k] + lc * 4));
+                float4 r = pre[k];
+                if (R.valid[k]) {
+                  r.x = fmaf(a.x + bias4.x, gg.x, r.x);
+                  r.y = fmaf(a.y + bias4.y, gg.y, r.y);
+                  r.z = fmaf(a.z + bias4.z, gg.z, r.z);
+                  r.w = fmaf(a.w + bias4.w, gg.w, r.w);
+                }
+                if (R.out[k]) {
+                  *reinterpret_cast<float4*>(R.out[k] + lc * 4) = r;
+                  if (R.out2[k]) *reinterpret_cast<uint2*>(R.out2[k] + lc * 2) = pack4_bf16(r);
+                }
+              }
+            }
+          }
+          __syncwarp();
+        };
+        float4 preA[8], preB[8];
+        float4 biasA, gateA, biasB, gateB;
+        load_ops(0, preA, biasA, gateA);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; c += 2) {
+          if (c * 32 >= ncols) break;
+          load_ops(c + 1, preB, biasB, gateB);
+          process(c, preA, biasA, gateA);
+          if ((c + 1) * 32 >= ncols) break;
+          load_ops(c + 2, preA, biasA, gateA);
+          process(c + 1, preB, biasB, gateB);
         }
       }
       tc_fence_before();
@@ -479,6 +519,11 @@ extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
   // Narrow outputs use 128-wide tiles; GEGLU needs the 128+128 packed 256 tile.
   const bool bn256 = (d->epi == E2B_EPI_GEGLU) || (d->N % 256 == 0) || (d->N > 1024);
   if (d->epi == E2B_EPI_GEGLU && d->N % 256) { e2b_set_kernel_error("gemm: GEGLU needs N %% 256 == 0 (N=%d)", d->N); return -1; }
+  if (d->epi != E2B_EPI_QKV && (d->N % 4 || d->ldo % 4 || (d->out_b16 && d->ldo_b16 % 4) || (d->resid && d->ldr % 4) || (d->add_table && d->ld_add % 4) ||
+                                (d->gate && d->gate_bstride % 4))) {
+    e2b_set_kernel_error("gemm: N and all leading dimensions must be multiples of 4");
+    return -1;
+  }
   if (d->epi == E2B_EPI_QKV && ((d->q_end | d->k_end | d->v_end) % 64 || d->rows_per_batch <= 0)) {
     e2b_set_kernel_error("gemm: QKV segment ends must be multiples of 64 and rows_per_batch > 0");
     return -1;
