@@ -71,16 +71,56 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
 // 31 FMAs with 8 independent accumulators.  (The first version -- global loads into a register ring -- was latency
 // bound: ncu 8 % DRAM, long-scoreboard 4.3 stalls/issue.)
 constexpr int DW_T = 64;            // output rows per tile
-constexpr int DW_C = 128;           // channels per tile == threads per CTA
-constexpr int DW_G = 8;             // outputs per register-window step
+constexpr int DW_C = 128;           // channels per tile
+constexpr int DW_G = 16;            // outputs per register-window step (two steps per thread)
 
 int make_tmap_generic(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims, const uint64_t* strides,
                       const uint32_t* box);
 
+// One thread: 32 consecutive outputs of one channel.  FULL = no row of the tile (halo included) is masked, which is every
+// tile except the last one of a sequence: the per-element length tests disappear from the hot loop.
+template <int KS, bool FULL>
+__device__ __forceinline__ void dwconv_rows(const float* __restrict__ xs, float* __restrict__ yp, const float (&w)[KS], float bs, int C,
+                                            int row0 /*first input row of xs[0]*/, int out0 /*first output row*/, int len, int N) {
+  constexpr int HALO = KS - 1, HALF = KS / 2;
+  auto ldx = [&](int j) -> float {
+    if (FULL) return xs[(size_t)j * DW_C];
+    return (row0 + j < len) ? xs[(size_t)j * DW_C] : 0.f;
+  };
+  float win[HALO + DW_G];
+#pragma unroll
+  for (int j = 0; j < HALO; ++j) win[j] = ldx(j);
+#pragma unroll 1
+  for (int g = 0; g < DW_T / 2; g += DW_G) {
+    if (!FULL && out0 + g >= N) break;
+#pragma unroll
+    for (int o = 0; o < DW_G; ++o) win[HALO + o] = ldx(HALO + g + o);
+    float acc[DW_G];
+#pragma unroll
+    for (int o = 0; o < DW_G; ++o) acc[o] = bs;
+#pragma unroll
+    for (int i = 0; i < KS; ++i)
+#pragma unroll
+      for (int o = 0; o < DW_G; ++o) acc[o] = fmaf(w[i], win[o + i], acc[o]);
+#pragma unroll
+    for (int o = 0; o < DW_G; ++o) {
+      if (FULL) {
+        yp[(size_t)(g + o) * C] = win[HALF + o] + silu(acc[o]);
+      } else {
+        const int r = out0 + g + o;
+        // the residual uses the UNMASKED x (e2_tts_crossatt3.py:1082: conv(x, mask) + x)
+        if (r < N) yp[(size_t)(g + o) * C] = (r < len) ? win[HALF + o] + silu(acc[o]) : xs[(size_t)(HALF + g + o) * DW_C];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < HALO; ++j) win[j] = win[j + DW_G];
+  }
+}
+
 template <int KS>
 __global__ void __launch_bounds__(2 * DW_C, 2) dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmx, float* __restrict__ y,
-                                                          const float* __restrict__ wt, const float* __restrict__ bias,
-                                                          const int* __restrict__ lens, int batch, int N, int C) {
+                                                                 const float* __restrict__ wt, const float* __restrict__ bias,
+                                                                 const int* __restrict__ lens, int batch, int N, int C) {
   constexpr int HALO = KS - 1, HALF = KS / 2, ROWS = DW_T + HALO;
   // no static shared memory: the dynamic window starts at offset 0 (128-byte alignment needed by the TMA destination) and
   // is used directly so loads stay LDS (a uintptr_t round-trip would make them generic LD.E)
@@ -104,6 +144,9 @@ __global__ void __launch_bounds__(2 * DW_C, 2) dwconv_tma_kernel(const __grid_co
   };
   if (threadIdx.x == 0 && (int)blockIdx.x < total) issue(blockIdx.x, 0);
 
+  float w[KS];
+  float bs = 0.f;
+  int wcc = -1;
   int it = 0;
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
     const int s = it & 1;
@@ -112,44 +155,19 @@ __global__ void __launch_bounds__(2 * DW_C, 2) dwconv_tma_kernel(const __grid_co
     const int c = cc * DW_C + tid;
     const int r0 = rt * DW_T;
     const int len = lens ? min(N, __ldg(lens + b)) : N;
-    mbar_wait(&full[s], (it >> 1) & 1);
-    if (c < C) {
-      float w[KS];
+    if (cc != wcc && c < C) {                     // taps change only with the channel chunk
 #pragma unroll
       for (int i = 0; i < KS; ++i) w[i] = __ldg(wt + (size_t)i * C + c);
-      const float bs = __ldg(bias + c);
-      const float* xs = buf + (size_t)s * ROWS * DW_C + tid;            // xs[j * DW_C] = x[r0 - HALF + j]
-      float* yb = y + ((size_t)b * N + r0) * C + c;
-      // rows >= len are masked to zero on input (rows outside [0, N) are already zero from the TMA fill)
-      auto ldx = [&](int j) -> float { return (r0 - HALF + j < len) ? xs[(size_t)j * DW_C] : 0.f; };
-      float win[HALO + DW_G];
+      bs = __ldg(bias + c);
+      wcc = cc;
+    }
+    mbar_wait(&full[s], (it >> 1) & 1);
+    if (c < C) {
       const int g0 = rhalf * (DW_T / 2);
-#pragma unroll
-      for (int j = 0; j < HALO; ++j) win[j] = ldx(g0 + j);
-#pragma unroll 1
-      for (int g = g0; g < g0 + DW_T / 2; g += DW_G) {
-        if (r0 + g >= N) break;
-#pragma unroll
-        for (int o = 0; o < DW_G; ++o) win[HALO + o] = ldx(HALO + g + o);
-        float acc[DW_G];
-#pragma unroll
-        for (int o = 0; o < DW_G; ++o) acc[o] = bs;
-#pragma unroll
-        for (int i = 0; i < KS; ++i)
-#pragma unroll
-          for (int o = 0; o < DW_G; ++o) acc[o] = fmaf(w[i], win[o + i], acc[o]);
-#pragma unroll
-        for (int o = 0; o < DW_G; ++o) {
-          const int r = r0 + g + o;
-          if (r < N) {
-            // the residual uses the UNMASKED x (e2_tts_crossatt3.py:1082: conv(x, mask) + x)
-            const float xc = xs[(size_t)(HALF + g + o) * DW_C];
-            yb[(size_t)(g + o) * C] = (r < len) ? xc + silu(acc[o]) : xc;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < HALO; ++j) win[j] = win[j + DW_G];
-      }
+      const float* xs = buf + (size_t)s * ROWS * DW_C + (size_t)g0 * DW_C + tid;      // xs[j * DW_C] = x[r0 + g0 - HALF + j]
+      float* yp = y + ((size_t)b * N + r0 + g0) * C + c;
+      if (r0 + DW_T + HALF <= len) dwconv_rows<KS, true>(xs, yp, w, bs, C, r0 + g0 - HALF, r0 + g0, len, N);
+      else dwconv_rows<KS, false>(xs, yp, w, bs, C, r0 + g0 - HALF, r0 + g0, len, N);
     }
     __syncthreads();     // everyone is done with buffer s before it is refilled two tiles later
   }
