@@ -34,6 +34,8 @@ typedef struct e2b_config {
   int heads, dim_head, frames_heads;      /* dim_head must be 64 */
   int num_channels, num_registers, kernel_size, notes, max_seq_len;
   int ff_mult;
+  int precision;                          /* 0 = bf16 tensor-core path (rel-L2 <= 1e-2); 1 = error-compensated "fp32" mode
+                                             (bf16 hi/lo operand pairs, 3 MMAs per product, exact fp32 attention; <= 1e-4) */
 } e2b_config;
 
 typedef struct e2b_tensor {

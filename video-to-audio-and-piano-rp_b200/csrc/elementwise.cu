@@ -22,7 +22,7 @@ __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __e
 // ------------------------------------------------------------------------------------------------ rmsnorm
 constexpr int NORM_MAX_V4 = 16;   // C <= 2048
 
-template <bool OUT_F32>
+template <int OUT_MODE>   // 0 bf16, 1 fp32, 2 bf16 (hi, lo) pair with lo at column + C
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, int ldx, void* __restrict__ yv, int ldy,
                                                       const float* __restrict__ scale, int scale_bstride, int rows_out_total,
                                                       int rows_per_batch, int skip_rows, int C, float sqrt_c) {
@@ -50,14 +50,23 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
     const int idx = lane + 32 * k;
     if (idx < nv) {
       const float4 s = __ldg(sc + idx);
-      if constexpr (OUT_F32) {
-        reinterpret_cast<float4*>(reinterpret_cast<float*>(yv) + (size_t)warp * ldy)[idx] =
-            make_float4(v[k].x * inv * s.x, v[k].y * inv * s.y, v[k].z * inv * s.z, v[k].w * inv * s.w);
+      const float4 o = make_float4(v[k].x * inv * s.x, v[k].y * inv * s.y, v[k].z * inv * s.z, v[k].w * inv * s.w);
+      if constexpr (OUT_MODE == 1) {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(yv) + (size_t)warp * ldy)[idx] = o;
       } else {
-        uint2 o;
-        o.x = pack_bf16(v[k].x * inv * s.x, v[k].y * inv * s.y);
-        o.y = pack_bf16(v[k].z * inv * s.z, v[k].w * inv * s.w);
-        reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(yv) + (size_t)warp * ldy)[idx] = o;
+        __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(yv) + (size_t)warp * ldy;
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+        uint2 hi;
+        hi.x = *reinterpret_cast<const uint32_t*>(&h0);
+        hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+        reinterpret_cast<uint2*>(yr)[idx] = hi;
+        if constexpr (OUT_MODE == 2) {
+          const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+          uint2 lo;
+          lo.x = pack_bf16(o.x - f0.x, o.y - f0.y);
+          lo.y = pack_bf16(o.z - f1.x, o.w - f1.y);
+          reinterpret_cast<uint2*>(yr + C)[idx] = lo;
+        }
       }
     }
   }
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(256) time_gemv_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) init_stream_kernel(float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_b16,
                                                           const float* __restrict__ regs, const float* __restrict__ src, int src_batches,
                                                           const unsigned char* __restrict__ drop, const float* __restrict__ add_table,
-                                                          int batch, int n, int R, int C, int regs_only) {
+                                                          int batch, int n, int R, int C, int regs_only, int ldb, int b16_split) {
   const int nv = C >> 2;
   const int rows = regs_only ? R : (R + n);
   const size_t total = (size_t)batch * rows * nv;
@@ -259,10 +268,19 @@ __global__ void __launch_bounds__(256) init_stream_kernel(float* __restrict__ ds
     const size_t o = ((size_t)b * (R + n) + pos) * C;
     reinterpret_cast<float4*>(dst + o)[v] = val;
     if (dst_b16) {
+      __nv_bfloat16* br = dst_b16 + ((size_t)b * (R + n) + pos) * ldb;
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(val.x, val.y), h1 = __floats2bfloat162_rn(val.z, val.w);
       uint2 u;
-      u.x = pack_bf16(val.x, val.y);
-      u.y = pack_bf16(val.z, val.w);
-      reinterpret_cast<uint2*>(dst_b16 + o)[v] = u;
+      u.x = *reinterpret_cast<const uint32_t*>(&h0);
+      u.y = *reinterpret_cast<const uint32_t*>(&h1);
+      reinterpret_cast<uint2*>(br)[v] = u;
+      if (b16_split > 0) {
+        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        uint2 lo;
+        lo.x = pack_bf16(val.x - f0.x, val.y - f0.y);
+        lo.y = pack_bf16(val.z - f1.x, val.w - f1.y);
+        reinterpret_cast<uint2*>(br + b16_split)[v] = lo;
+      }
     }
   }
 }
@@ -374,18 +392,17 @@ static int check_launch(const char* what) {
 using namespace e2b;
 
 extern "C" int e2b_rmsnorm_launch(const float* x, int ldx, void* y, int ldy, const float* scale, int scale_bstride, int batch,
-                                  int rows_per_batch, int skip_rows, int C, int out_f32, cudaStream_t stream) {
+                                  int rows_per_batch, int skip_rows, int C, int out_mode, cudaStream_t stream) {
   if (C % 4 || C > NORM_MAX_V4 * 128 || ldx % 4 || ldy % 4) { e2b_set_kernel_error("rmsnorm: C=%d unsupported", C); return -1; }
+  if (out_mode == 2 && ldy < 2 * C) { e2b_set_kernel_error("rmsnorm: split output needs ldy >= 2C"); return -1; }
   const int rows_out = batch * (rows_per_batch - skip_rows);
   if (rows_out <= 0) return 0;
   const int blocks = (rows_out + 7) / 8;
-  ProfScope ps(stream, "rmsnorm", rows_out, C, 0, 3.0 * rows_out * C, (double)rows_out * C * (out_f32 ? 8.0 : 6.0));
-  if (out_f32)
-    rmsnorm_kernel<true><<<blocks, 256, 0, stream>>>(x, ldx, y, ldy, scale, scale_bstride, rows_out, rows_per_batch, skip_rows, C,
-                                                     sqrtf((float)C));
-  else
-    rmsnorm_kernel<false><<<blocks, 256, 0, stream>>>(x, ldx, y, ldy, scale, scale_bstride, rows_out, rows_per_batch, skip_rows, C,
-                                                      sqrtf((float)C));
+  ProfScope ps(stream, "rmsnorm", rows_out, C, 0, 3.0 * rows_out * C, (double)rows_out * C * (out_mode == 1 ? 8.0 : (out_mode == 2 ? 8.0 : 6.0)));
+  const float sq = sqrtf((float)C);
+  if (out_mode == 1) rmsnorm_kernel<1><<<blocks, 256, 0, stream>>>(x, ldx, y, ldy, scale, scale_bstride, rows_out, rows_per_batch, skip_rows, C, sq);
+  else if (out_mode == 2) rmsnorm_kernel<2><<<blocks, 256, 0, stream>>>(x, ldx, y, ldy, scale, scale_bstride, rows_out, rows_per_batch, skip_rows, C, sq);
+  else rmsnorm_kernel<0><<<blocks, 256, 0, stream>>>(x, ldx, y, ldy, scale, scale_bstride, rows_out, rows_per_batch, skip_rows, C, sq);
   return check_launch("rmsnorm");
 }
 
@@ -431,18 +448,24 @@ extern "C" int e2b_time_gemv_launch(const float* tcond, int nt, int dim, const f
   return check_launch("time_gemv");
 }
 
-extern "C" int e2b_init_stream_launch(float* dst, void* dst_b16, const float* registers, const float* src, int src_batches,
-                                      const unsigned char* drop, const float* add_table, int batch, int n, int R, int C,
-                                      cudaStream_t stream) {
-  if (C % 4) { e2b_set_kernel_error("init_stream: C %% 4 != 0"); return -1; }
+extern "C" int e2b_init_stream_split_launch(float* dst, void* dst_b16, int ldb, int b16_split, const float* registers, const float* src,
+                                            int src_batches, const unsigned char* drop, const float* add_table, int batch, int n, int R, int C,
+                                            cudaStream_t stream) {
+  if (C % 4 || ldb % 4 || b16_split % 4) { e2b_set_kernel_error("init_stream: C / ldb / split must be multiples of 4"); return -1; }
   const int regs_only = (src_batches < 0);
   const size_t total = (size_t)batch * (regs_only ? R : R + n) * (C / 4);
   if (!total) return 0;
   ProfScope ps(stream, "init_stream", (long long)batch * (regs_only ? R : R + n), C, 0, 0.0, (double)total * 16.0 * (dst_b16 ? 1.5 : 1.0));
   init_stream_kernel<<<grid_for(total, 256), 256, 0, stream>>>(dst, reinterpret_cast<__nv_bfloat16*>(dst_b16), registers, src,
                                                                src_batches > 0 ? src_batches : 1, drop, add_table, batch, n, R, C,
-                                                               regs_only);
+                                                               regs_only, ldb > 0 ? ldb : C, b16_split);
   return check_launch("init_stream");
+}
+
+extern "C" int e2b_init_stream_launch(float* dst, void* dst_b16, const float* registers, const float* src, int src_batches,
+                                      const unsigned char* drop, const float* add_table, int batch, int n, int R, int C,
+                                      cudaStream_t stream) {
+  return e2b_init_stream_split_launch(dst, dst_b16, C, 0, registers, src, src_batches, drop, add_table, batch, n, R, C, stream);
 }
 
 namespace e2b {
@@ -460,6 +483,27 @@ extern "C" int e2b_transpose_launch(const float* src, float* dst, int rows, int 
   if (!total) return 0;
   e2b::transpose_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, dst, rows, cols);
   return check_launch("transpose");
+}
+
+namespace e2b {
+__global__ void __launch_bounds__(256) cast_part_kernel(const float* __restrict__ src, int lds, __nv_bfloat16* __restrict__ dst, int ldd,
+                                                        size_t rows, int C, int W, int part) {
+  const size_t total = rows * W;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = idx % W;
+    const size_t r = idx / W;
+    float v = c < C ? src[r * lds + c] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    dst[r * ldd + c] = part == 0 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+}  // namespace e2b
+
+extern "C" int e2b_cast_part_launch(const float* src, int lds, void* dst, int ldd, int rows, int C, int W, int part, cudaStream_t stream) {
+  const size_t total = (size_t)rows * W;
+  if (!total) return 0;
+  e2b::cast_part_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, (size_t)rows, C, W, part);
+  return check_launch("cast_part");
 }
 
 extern "C" int e2b_cast_pad_launch(const float* src, int lds, void* dst, int ldd, int rows, int C, cudaStream_t stream) {

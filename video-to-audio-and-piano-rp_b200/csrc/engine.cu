@@ -53,6 +53,7 @@ struct e2b_handle {
   int* tm_act = nullptr;
 
   // prepared shape
+  bool f32 = false;                // error-compensated mode: bf16 A operands are (hi, lo) pairs, weights [W_hi|W_hi|W_lo]
   int B = 0, n = 0, nc = 0, P = 0, Pctx = 0, N = 0, Bt = 0, Npad = 0, ncpad = 0;
   size_t M = 0;
   bool conditions_set = false;
@@ -60,6 +61,8 @@ struct e2b_handle {
   bf16 *xb = nullptr, *textb = nullptr, *framesb = nullptr, *xtmpb = nullptr, *nb = nullptr, *qk = nullptr, *vt = nullptr, *ob = nullptr,
        *hb = nullptr, *ybf = nullptr, *finalb = nullptr, *fin = nullptr, *ctxb = nullptr;
   std::vector<bf16*> skipb, k2, vt2;
+  float *qkf = nullptr, *vf = nullptr;      // fp32 q/k and v (fp32 mode)
+  std::vector<float*> k2f, v2f;
   float *hg = nullptr, *fr0 = nullptr, *clip = nullptr, *pred = nullptr, *gam = nullptr, *tcond = nullptr, *times_dev = nullptr;
   double* apg_scratch = nullptr;
   int *lens_dev = nullptr, *ctx_lens_dev = nullptr;
@@ -146,30 +149,65 @@ int copy_f32(e2b_handle* h, const WMap& w, const std::string& name, float** dst,
   return 0;
 }
 
-// dst rows [row0, row0+rows) of a bf16 [*, ldd] matrix <- src fp32 rows [srow0, ...) of [*, K]
-int cast_rows(e2b_handle* h, const float* src, int K, int srow0, bf16* dst, int ldd, int row0, int rows, cudaStream_t st) {
-  CK(e2b_cast_pad_launch(src + (size_t)srow0 * K, K, dst + (size_t)row0 * ldd, ldd, rows, K, st));
+// K-dimension expansion of the error-compensated mode: a block of C input columns (padded to W) becomes [hi | hi | lo].
+inline int kx(const e2b_handle* h, int K) { return h->f32 ? 3 * K : K; }
+
+// dst rows [drow0, drow0+rows), columns from dcol0 <- src fp32 rows [srow0, ...), columns [scol0, scol0+C) (zero-padded to W).
+// Returns the next free destination column.
+int cast_block(e2b_handle* h, const float* src, int lds, int srow0, int scol0, int C, int W, bf16* dst, int ldd, int drow0, int dcol0, int rows,
+               cudaStream_t st, int* next_col) {
+  const float* sp = src + (size_t)srow0 * lds + scol0;
+  bf16* dp = dst + (size_t)drow0 * ldd + dcol0;
+  CK(e2b_cast_part_launch(sp, lds, dp, ldd, rows, C, W, 0, st));
+  if (h->f32) {
+    CK(e2b_cast_part_launch(sp, lds, dp + W, ldd, rows, C, W, 0, st));
+    CK(e2b_cast_part_launch(sp, lds, dp + 2 * W, ldd, rows, C, W, 1, st));
+  }
+  *next_col = dcol0 + kx(h, W);
   return 0;
 }
 
-int pack_linear(e2b_handle* h, const WMap& w, const std::string& name, bf16** dst, int out_f, int in_f, cudaStream_t st, int ldd = 0) {
+struct KBlock { int C, W; };   // source columns, padded width
+
+// rows [srow0, srow0+rows) of a [*, in_f] fp32 weight -> rows [drow0, ...) of the packed bf16 matrix, K split into blocks
+int cast_weight_rows(e2b_handle* h, const float* src, int in_f, int srow0, int rows, bf16* dst, int ldd, int drow0,
+                     const std::vector<KBlock>& blocks, cudaStream_t st) {
+  int scol = 0, dcol = 0;
+  for (const KBlock& kb : blocks) {
+    if (cast_block(h, src, in_f, srow0, scol, kb.C, kb.W, dst, ldd, drow0, dcol, rows, st, &dcol)) return -1;
+    scol += kb.C;
+  }
+  return 0;
+}
+
+int packed_k(const e2b_handle* h, const std::vector<KBlock>& blocks) {
+  int k = 0;
+  for (const KBlock& b : blocks) k += kx(h, b.W);
+  return k;
+}
+
+int pack_linear(e2b_handle* h, const WMap& w, const std::string& name, bf16** dst, int out_f, int in_f, cudaStream_t st,
+                std::vector<KBlock> blocks = {}) {
   const e2b_tensor* t;
   if (need(h, w, name, &t, out_f, in_f)) return -1;
-  if (!ldd) ldd = in_f;
+  if (blocks.empty()) blocks = {{in_f, in_f}};
+  const int ldd = packed_k(h, blocks);
   DA(h->wallocs, *dst, (size_t)out_f * ldd);
-  return cast_rows(h, t->dev, in_f, 0, *dst, ldd, 0, out_f, st);
+  return cast_weight_rows(h, t->dev, in_f, 0, out_f, *dst, ldd, 0, blocks, st);
 }
 
 // [Wq; Wk; Wv; Wgate] (or a subset) -> one bf16 matrix
 int pack_concat(e2b_handle* h, const WMap& w, const std::vector<std::pair<std::string, int>>& parts, int in_f, bf16** dst, cudaStream_t st) {
   int rows = 0;
   for (auto& p : parts) rows += p.second;
-  DA(h->wallocs, *dst, (size_t)rows * in_f);
+  const std::vector<KBlock> blocks = {{in_f, in_f}};
+  const int ldd = packed_k(h, blocks);
+  DA(h->wallocs, *dst, (size_t)rows * ldd);
   int r = 0;
   for (auto& p : parts) {
     const e2b_tensor* t;
     if (need(h, w, p.first, &t, p.second, in_f)) return -1;
-    if (cast_rows(h, t->dev, in_f, 0, *dst, in_f, r, p.second, st)) return -1;
+    if (cast_weight_rows(h, t->dev, in_f, 0, p.second, *dst, ldd, r, blocks, st)) return -1;
     r += p.second;
   }
   return 0;
@@ -180,11 +218,13 @@ int pack_geglu(e2b_handle* h, const WMap& w, const std::string& base, int dim, i
   const e2b_tensor *tw, *tb;
   if (need(h, w, base + ".weight", &tw, 2 * inner, dim) || need(h, w, base + ".bias", &tb, 2 * inner)) return -1;
   if (inner % 128) return fail(h, "GEGLU inner dim %d must be a multiple of 128", inner);
-  DA(h->wallocs, *wd, (size_t)2 * inner * dim);
+  const std::vector<KBlock> blocks = {{dim, dim}};
+  const int ldd = packed_k(h, blocks);
+  DA(h->wallocs, *wd, (size_t)2 * inner * ldd);
   DA(h->wallocs, *bd, (size_t)2 * inner);
   for (int t = 0; t < inner / 128; ++t) {
-    if (cast_rows(h, tw->dev, dim, t * 128, *wd, dim, t * 256, 128, st)) return -1;
-    if (cast_rows(h, tw->dev, dim, inner + t * 128, *wd, dim, t * 256 + 128, 128, st)) return -1;
+    if (cast_weight_rows(h, tw->dev, dim, t * 128, 128, *wd, ldd, t * 256, blocks, st)) return -1;
+    if (cast_weight_rows(h, tw->dev, dim, inner + t * 128, 128, *wd, ldd, t * 256 + 128, blocks, st)) return -1;
     CU(cudaMemcpyAsync(*bd + t * 256, tb->dev + t * 128, 128 * 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(*bd + t * 256 + 128, tb->dev + inner + t * 128, 128 * 4, cudaMemcpyDeviceToDevice, st));
   }
@@ -219,19 +259,53 @@ void free_workspace(e2b_handle* h) {
   h->skipb.clear();
   h->k2.clear();
   h->vt2.clear();
+  h->k2f.clear();
+  h->v2f.clear();
   h->B = h->n = h->nc = h->P = 0;
   h->gam_capacity = 0;
   h->conditions_set = false;
 }
 
 // ------------------------------------------------------------------------------------------ gemm descriptor helpers
-e2b_gemm_desc gd(size_t M, int N, int K, const void* a, int lda, const void* w) {
+// A logical bf16 A operand [rows, C].  In the error-compensated mode it is stored as [rows, 2C] = (hi | lo) and consumed as
+// the three K-concatenated sources (hi, lo, hi) against weights packed (W_hi | W_hi | W_lo).
+struct Src { const bf16* p; int C; };
+inline int ldb(const e2b_handle* h, int C) { return h->f32 ? 2 * C : C; }     // leading dimension of a bf16 A-operand buffer
+inline int spl(const e2b_handle* h, int C) { return h->f32 ? C : 0; }         // `split` offset for its producers
+
+e2b_gemm_desc gdesc(const e2b_handle* h, size_t M, int N, std::initializer_list<Src> srcs, const void* w) {
   e2b_gemm_desc d;
   memset(&d, 0, sizeof(d));
-  d.M = (int)M; d.N = N; d.K = K;
-  d.num_src = 1; d.a[0] = a; d.lda[0] = lda; d.ka[0] = K;
-  d.w = w; d.ldw = K;
+  d.M = (int)M; d.N = N;
+  int n = 0, K = 0;
+  for (const Src& s : srcs) {
+    if (!h->f32) {
+      d.a[n] = s.p; d.lda[n] = s.C; d.ka[n] = s.C; ++n;
+    } else {
+      d.a[n] = s.p; d.a[n + 1] = s.p + s.C; d.a[n + 2] = s.p;
+      for (int i = 0; i < 3; ++i) { d.lda[n + i] = 2 * s.C; d.ka[n + i] = s.C; }
+      n += 3;
+    }
+    K += kx(h, s.C);
+  }
+  d.num_src = n; d.K = K; d.w = w; d.ldw = K;
   return d;
+}
+
+// fp32 activations -> bf16 A operand (columns zero-padded C -> W)
+int cast_act(e2b_handle* h, const float* src, int lds, bf16* dst, int C, int W, size_t rows, cudaStream_t st) {
+  if (!h->f32) {
+    CK(e2b_cast_pad_launch(src, lds, dst, W, (int)rows, C, st));
+  } else {
+    CK(e2b_cast_part_launch(src, lds, dst, 2 * W, (int)rows, C, W, 0, st));
+    CK(e2b_cast_part_launch(src, lds, dst + W, 2 * W, (int)rows, C, W, 1, st));
+  }
+  return 0;
+}
+
+int norm(e2b_handle* h, const float* x, int C, bf16* y, const float* scale, int bstride, int batch, int skip, cudaStream_t st) {
+  CK(e2b_rmsnorm_launch(x, C, y, ldb(h, C), scale, bstride, batch, h->N, skip, C, h->f32 ? 2 : 0, st));
+  return 0;
 }
 
 struct GamRef { const float* p; int bstride; };
@@ -246,28 +320,68 @@ int compute_time_tables(e2b_handle* h, const float* times_host, int nt, cudaStre
   return 0;
 }
 
-int self_attention(e2b_handle* h, int C, int heads, const bf16* w_qkv, const float* hg_b, const bf16* nb, cudaStream_t st) {
+// q/k/v(+gate) projection of `nb` followed by attention; result in h->ob.  kv = nullptr: self attention over `batch`
+// sequences; otherwise cross attention to the precomputed context K/V of layer `l`.
+int attention_block(e2b_handle* h, int C, int heads, const bf16* w_q, const float* hg_b, int batch, int layer_ctx, cudaStream_t st) {
   const int HDs = heads * 64;
-  e2b_gemm_desc d = gd(h->M, 3 * HDs + heads, C, nb, C, w_qkv);
+  const bool cross = layer_ctx >= 0;
+  const size_t rows = (size_t)batch * h->N;
+  const int qcols = cross ? HDs : 2 * HDs;                       // q | k side by side for self attention
+  e2b_gemm_desc d = gdesc(h, rows, (cross ? HDs : 3 * HDs) + heads, {{h->nb, C}}, w_q);
   d.epi = E2B_EPI_QKV;
-  d.out = h->qk; d.ldo = 2 * HDs;
-  d.q_end = HDs; d.k_end = 2 * HDs; d.v_end = 3 * HDs;
+  d.ldo = qcols;
+  d.q_end = HDs; d.k_end = cross ? HDs : 2 * HDs; d.v_end = cross ? HDs : 3 * HDs;
   d.q_scale = 0.125f;
   d.rope = h->rope; d.pos_off = 0; d.rows_per_batch = h->N;
-  d.vt = h->vt; d.vt_ld = h->Npad; d.heads_v = heads;
   d.hgate = h->hg; d.hgate_ld = heads; d.hgate_bias = hg_b;
+  if (!h->f32) {
+    d.out = h->qk;
+    d.vt = h->vt; d.vt_ld = h->Npad; d.heads_v = heads;
+  } else {
+    d.out = h->qkf; d.qk_f32 = h->qkf; d.v_f32 = h->vf; d.v_f32_ld = HDs; d.heads_v = heads;
+  }
   CK(e2b_gemm_launch(&d, st));
-  e2b_attn_desc a;
-  memset(&a, 0, sizeof(a));
-  a.batch = h->Bt; a.heads = heads; a.q_rows_per_batch = h->N; a.kv_rows_per_batch = h->N;
-  a.q = h->qk; a.ldq = 2 * HDs; a.q_col0 = 0;
-  a.k = h->qk; a.ldk = 2 * HDs; a.k_col0 = HDs;
-  a.vt = h->vt; a.vt_ld = h->Npad;
-  a.kv_lens = h->lens_dev; a.kv_lens_add = 0;
-  a.hgate = h->hg; a.hgate_ld = heads;
-  a.out = h->ob; a.ldo = HDs;
-  a.softclamp = 50.0f;
-  CK(e2b_attention_launch(&a, st));
+  if (!h->f32) {
+    e2b_attn_desc a;
+    memset(&a, 0, sizeof(a));
+    a.batch = batch; a.heads = heads; a.q_rows_per_batch = h->N;
+    a.q = h->qk; a.ldq = qcols; a.q_col0 = 0;
+    if (cross) {
+      a.kv_rows_per_batch = h->nc;
+      a.k = h->k2[layer_ctx]; a.ldk = HDs; a.k_col0 = 0;
+      a.vt = h->vt2[layer_ctx]; a.vt_ld = h->ncpad;
+      a.kv_batch_mod = h->B; a.kv_lens = h->ctx_lens_dev;
+    } else {
+      a.kv_rows_per_batch = h->N;
+      a.k = h->qk; a.ldk = qcols; a.k_col0 = HDs;
+      a.vt = h->vt; a.vt_ld = h->Npad;
+      a.kv_lens = h->lens_dev;
+    }
+    a.hgate = h->hg; a.hgate_ld = heads;
+    a.out = h->ob; a.ldo = HDs;
+    a.softclamp = 50.0f;
+    CK(e2b_attention_launch(&a, st));
+  } else {
+    e2b_attn_f32_desc a;
+    memset(&a, 0, sizeof(a));
+    a.batch = batch; a.heads = heads; a.q_rows_per_batch = h->N;
+    a.q = h->qkf; a.ldq = qcols; a.q_col0 = 0;
+    if (cross) {
+      a.kv_rows_per_batch = h->nc;
+      a.k = h->k2f[layer_ctx]; a.ldk = HDs; a.k_col0 = 0;
+      a.v = h->v2f[layer_ctx]; a.ldv = HDs; a.v_col0 = 0;
+      a.kv_batch_mod = h->B; a.kv_lens = h->ctx_lens_dev;
+    } else {
+      a.kv_rows_per_batch = h->N;
+      a.k = h->qkf; a.ldk = qcols; a.k_col0 = HDs;
+      a.v = h->vf; a.ldv = HDs; a.v_col0 = 0;
+      a.kv_lens = h->lens_dev;
+    }
+    a.hgate = h->hg; a.hgate_ld = heads;
+    a.out = h->ob; a.ldo = 2 * HDs; a.out_split = HDs;
+    a.softclamp = 50.0f;
+    CK(e2b_attention_f32_launch(&a, st));
+  }
   return 0;
 }
 
@@ -275,26 +389,26 @@ int side_stream(e2b_handle* h, float* (&s)[2], bf16* sb, int C, int heads, int i
   const int HDs = heads * 64;
   CK(e2b_dwconv_launch(s[0], s[1], w.conv_w, w.conv_b, h->lens_dev, h->Bt, h->N, C, h->cfg.kernel_size, st));
   std::swap(s[0], s[1]);
-  CK(e2b_rmsnorm_launch(s[0], C, h->nb, C, w.g1, 0, h->Bt, h->N, 0, C, 0, st));
-  if (self_attention(h, C, heads, w.qkv_w, w.hg_b, h->nb, st)) return -1;
+  if (norm(h, s[0], C, h->nb, w.g1, 0, h->Bt, 0, st)) return -1;
+  if (attention_block(h, C, heads, w.qkv_w, w.hg_b, h->Bt, -1, st)) return -1;
   {
-    e2b_gemm_desc d = gd(h->M, C, HDs, h->ob, HDs, w.out_w);
+    e2b_gemm_desc d = gdesc(h, h->M, C, {{h->ob, HDs}}, w.out_w);
     d.epi = E2B_EPI_RESID;
     d.out = s[0]; d.ldo = C; d.resid = s[0]; d.ldr = C;
     d.lens = h->lens_dev; d.rows_per_batch = h->N;
     CK(e2b_gemm_launch(&d, st));
   }
-  CK(e2b_rmsnorm_launch(s[0], C, h->nb, C, w.g2, 0, h->Bt, h->N, 0, C, 0, st));
+  if (norm(h, s[0], C, h->nb, w.g2, 0, h->Bt, 0, st)) return -1;
   {
-    e2b_gemm_desc d = gd(h->M, 2 * inner, C, h->nb, C, w.ff1_w);
-    d.epi = E2B_EPI_GEGLU; d.bias = w.ff1_b; d.out = h->hb; d.ldo = inner;
+    e2b_gemm_desc d = gdesc(h, h->M, 2 * inner, {{h->nb, C}}, w.ff1_w);
+    d.epi = E2B_EPI_GEGLU; d.bias = w.ff1_b; d.out = h->hb; d.ldo = ldb(h, inner); d.split = spl(h, inner);
     CK(e2b_gemm_launch(&d, st));
   }
   {
-    e2b_gemm_desc d = gd(h->M, C, inner, h->hb, inner, w.ff2_w);
+    e2b_gemm_desc d = gdesc(h, h->M, C, {{h->hb, inner}}, w.ff2_w);
     d.epi = E2B_EPI_RESID; d.bias = w.ff2_b;
     d.out = s[0]; d.ldo = C; d.resid = s[0]; d.ldr = C;
-    d.out_b16 = sb; d.ldo_b16 = C;
+    d.out_b16 = sb; d.ldo_b16 = ldb(h, C); d.split = spl(h, C);
     CK(e2b_gemm_launch(&d, st));
   }
   return 0;
@@ -306,7 +420,8 @@ int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
   const int dim = c.dim, dt = c.dim_text, df = c.dim_frames, H = c.heads;
   const int HD = h->HD;
   const size_t M = h->M;
-  const size_t Mc = (size_t)h->Pctx * h->B * h->N;
+  const int ctx_batch = h->Pctx * h->B;
+  const size_t Mc = (size_t)ctx_batch * h->N;
   auto G = [&](int layer, int which) { return gam.p + (size_t)(layer * 6 + which) * dim; };
 
   for (int l = 0; l < c.depth; ++l) {
@@ -317,35 +432,25 @@ int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
     // cross condition (all three read the pre-update bf16 copies)
     bf16* xnew_b = (l < c.depth / 2) ? h->skipb[l] : h->xtmpb;
     {
-      e2b_gemm_desc d = gd(M, dim, dim + dt + df, h->xb, dim, w.tfa_w);
-      d.num_src = 3;
-      d.ka[0] = dim;
-      d.a[1] = h->textb; d.lda[1] = dt; d.ka[1] = dt;
-      d.a[2] = h->framesb; d.lda[2] = df; d.ka[2] = df;
+      e2b_gemm_desc d = gdesc(h, M, dim, {{h->xb, dim}, {h->textb, dt}, {h->framesb, df}}, w.tfa_w);
       d.epi = E2B_EPI_RESID;
       d.out = h->x[0]; d.ldo = dim; d.resid = h->x[0]; d.ldr = dim;
-      d.out_b16 = xnew_b; d.ldo_b16 = dim;
+      d.out_b16 = xnew_b; d.ldo_b16 = ldb(h, dim); d.split = spl(h, dim);
       CK(e2b_gemm_launch(&d, st));
     }
     if (w.at_w) {
-      e2b_gemm_desc d = gd(M, dt, dim + dt, h->xb, dim, w.at_w);
-      d.num_src = 2; d.ka[0] = dim;
-      d.a[1] = h->textb; d.lda[1] = dt; d.ka[1] = dt;
+      e2b_gemm_desc d = gdesc(h, M, dt, {{h->xb, dim}, {h->textb, dt}}, w.at_w);
       d.epi = E2B_EPI_RESID;
       d.out = h->text[0]; d.ldo = dt; d.resid = h->text[0]; d.ldr = dt;
       CK(e2b_gemm_launch(&d, st));
-      e2b_gemm_desc e = gd(M, df, dim + df, h->xb, dim, w.af_w);
-      e.num_src = 2; e.ka[0] = dim;
-      e.a[1] = h->framesb; e.lda[1] = df; e.ka[1] = df;
+      e2b_gemm_desc e = gdesc(h, M, df, {{h->xb, dim}, {h->framesb, df}}, w.af_w);
       e.epi = E2B_EPI_RESID;
       e.out = h->frames[0]; e.ldo = df; e.resid = h->frames[0]; e.ldr = df;
       CK(e2b_gemm_launch(&e, st));
     }
     // U-Net skip
     if (l >= c.depth / 2) {
-      e2b_gemm_desc d = gd(M, dim, 2 * dim, h->xtmpb, dim, w.skip_w);
-      d.num_src = 2; d.ka[0] = dim;
-      d.a[1] = h->skipb[c.depth - 1 - l]; d.lda[1] = dim; d.ka[1] = dim;
+      e2b_gemm_desc d = gdesc(h, M, dim, {{h->xtmpb, dim}, {h->skipb[c.depth - 1 - l], dim}}, w.skip_w);
       d.epi = E2B_EPI_F32;
       d.out = h->x[0]; d.ldo = dim;
       CK(e2b_gemm_launch(&d, st));
@@ -353,10 +458,10 @@ int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
     // audio stream
     CK(e2b_dwconv_launch(h->x[0], h->x[1], w.conv_w, w.conv_b, h->lens_dev, h->Bt, h->N, dim, c.kernel_size, st));
     std::swap(h->x[0], h->x[1]);
-    CK(e2b_rmsnorm_launch(h->x[0], dim, h->nb, dim, G(l, 0), gam.bstride, h->Bt, h->N, 0, dim, 0, st));
-    if (self_attention(h, dim, H, w.qkv_w, w.hg_b, h->nb, st)) return -1;
+    if (norm(h, h->x[0], dim, h->nb, G(l, 0), gam.bstride, h->Bt, 0, st)) return -1;
+    if (attention_block(h, dim, H, w.qkv_w, w.hg_b, h->Bt, -1, st)) return -1;
     {
-      e2b_gemm_desc d = gd(M, dim, HD, h->ob, HD, w.out_w);
+      e2b_gemm_desc d = gdesc(h, M, dim, {{h->ob, HD}}, w.out_w);
       d.epi = E2B_EPI_RESID;
       d.out = h->x[0]; d.ldo = dim; d.resid = h->x[0]; d.ldr = dim;
       d.gate = G(l, 1); d.gate_bstride = gam.bstride;
@@ -365,46 +470,27 @@ int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
     }
     // cross attention to the T5 context: only for passes whose context is live (a zero context gives exactly 0)
     if (Mc > 0) {
-      CK(e2b_rmsnorm_launch(h->x[0], dim, h->nb, dim, G(l, 2), gam.bstride, h->Pctx * h->B, h->N, 0, dim, 0, st));
-      e2b_gemm_desc d = gd(Mc, HD + H, dim, h->nb, dim, w.q2_w);
-      d.epi = E2B_EPI_QKV;
-      d.out = h->qk; d.ldo = HD;
-      d.q_end = HD; d.k_end = HD; d.v_end = HD;
-      d.q_scale = 0.125f;
-      d.rope = h->rope; d.pos_off = 0; d.rows_per_batch = h->N;
-      d.hgate = h->hg; d.hgate_ld = H; d.hgate_bias = w.hg2_b;
-      CK(e2b_gemm_launch(&d, st));
-      e2b_attn_desc a;
-      memset(&a, 0, sizeof(a));
-      a.batch = h->Pctx * h->B; a.heads = H; a.q_rows_per_batch = h->N; a.kv_rows_per_batch = h->nc;
-      a.q = h->qk; a.ldq = HD; a.q_col0 = 0;
-      a.k = h->k2[l]; a.ldk = HD; a.k_col0 = 0;
-      a.vt = h->vt2[l]; a.vt_ld = h->ncpad;
-      a.kv_batch_mod = h->B;
-      a.kv_lens = h->ctx_lens_dev; a.kv_lens_add = 0;
-      a.hgate = h->hg; a.hgate_ld = H;
-      a.out = h->ob; a.ldo = HD;
-      a.softclamp = 50.0f;
-      CK(e2b_attention_launch(&a, st));
-      e2b_gemm_desc o = gd(Mc, dim, HD, h->ob, HD, w.out2_w);
+      if (norm(h, h->x[0], dim, h->nb, G(l, 2), gam.bstride, ctx_batch, 0, st)) return -1;
+      if (attention_block(h, dim, H, w.q2_w, w.hg2_b, ctx_batch, l, st)) return -1;
+      e2b_gemm_desc o = gdesc(h, Mc, dim, {{h->ob, HD}}, w.out2_w);
       o.epi = E2B_EPI_RESID;
       o.out = h->x[0]; o.ldo = dim; o.resid = h->x[0]; o.ldr = dim;
       o.gate = G(l, 3); o.gate_bstride = gam.bstride;
       o.lens = h->lens_dev; o.rows_per_batch = h->N;
       CK(e2b_gemm_launch(&o, st));
     }
-    CK(e2b_rmsnorm_launch(h->x[0], dim, h->nb, dim, G(l, 4), gam.bstride, h->Bt, h->N, 0, dim, 0, st));
+    if (norm(h, h->x[0], dim, h->nb, G(l, 4), gam.bstride, h->Bt, 0, st)) return -1;
     {
-      e2b_gemm_desc d = gd(M, 2 * h->inner, dim, h->nb, dim, w.ff1_w);
-      d.epi = E2B_EPI_GEGLU; d.bias = w.ff1_b; d.out = h->hb; d.ldo = h->inner;
+      e2b_gemm_desc d = gdesc(h, M, 2 * h->inner, {{h->nb, dim}}, w.ff1_w);
+      d.epi = E2B_EPI_GEGLU; d.bias = w.ff1_b; d.out = h->hb; d.ldo = ldb(h, h->inner); d.split = spl(h, h->inner);
       CK(e2b_gemm_launch(&d, st));
     }
     {
-      e2b_gemm_desc d = gd(M, dim, h->inner, h->hb, h->inner, w.ff2_w);
+      e2b_gemm_desc d = gdesc(h, M, dim, {{h->hb, h->inner}}, w.ff2_w);
       d.epi = E2B_EPI_RESID; d.bias = w.ff2_b;
       d.out = h->x[0]; d.ldo = dim; d.resid = h->x[0]; d.ldr = dim;
       d.gate = G(l, 5); d.gate_bstride = gam.bstride; d.rows_per_batch = h->N;
-      d.out_b16 = h->xb; d.ldo_b16 = dim;
+      d.out_b16 = h->xb; d.ldo_b16 = ldb(h, dim); d.split = spl(h, dim);
       CK(e2b_gemm_launch(&d, st));
     }
   }
@@ -415,10 +501,11 @@ int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
 int init_streams_from_state(e2b_handle* h, cudaStream_t st) {
   const e2b_config& c = h->cfg;
   const int R = c.num_registers;
-  CK(e2b_init_stream_launch(h->x[0], h->xb, h->registers, nullptr, -1, nullptr, nullptr, h->Bt, h->n, R, c.dim, st));
-  e2b_gemm_desc d = gd((size_t)h->Bt * h->n, c.dim, c.num_channels, h->ybf, c.num_channels, h->proj_in_w);
+  CK(e2b_init_stream_split_launch(h->x[0], h->xb, ldb(h, c.dim), spl(h, c.dim), h->registers, nullptr, -1, nullptr, nullptr, h->Bt, h->n, R,
+                                  c.dim, st));
+  e2b_gemm_desc d = gdesc(h, (size_t)h->Bt * h->n, c.dim, {{h->ybf, c.num_channels}}, h->proj_in_w);
   d.epi = E2B_EPI_F32; d.bias = h->proj_in_b;
-  d.out = h->x[0]; d.ldo = c.dim; d.out_b16 = h->xb; d.ldo_b16 = c.dim;
+  d.out = h->x[0]; d.ldo = c.dim; d.out_b16 = h->xb; d.ldo_b16 = ldb(h, c.dim); d.split = spl(h, c.dim);
   d.rpb_in = h->n; d.rpb_out = h->N; d.row_off = R;
   d.add_table = h->abs_pos; d.ld_add = c.dim;
   CK(e2b_gemm_launch(&d, st));
@@ -429,8 +516,8 @@ int init_streams_from_state(e2b_handle* h, cudaStream_t st) {
 
 int pred_head(e2b_handle* h, float* pred, cudaStream_t st) {
   const e2b_config& c = h->cfg;
-  CK(e2b_rmsnorm_launch(h->x[0], c.dim, h->finalb, c.dim, h->final_g, 0, h->Bt, h->N, c.num_registers, c.dim, 0, st));
-  e2b_gemm_desc d = gd((size_t)h->Bt * h->n, c.num_channels, c.dim, h->finalb, c.dim, h->to_pred_w);
+  if (norm(h, h->x[0], c.dim, h->finalb, h->final_g, 0, h->Bt, c.num_registers, st)) return -1;
+  e2b_gemm_desc d = gdesc(h, (size_t)h->Bt * h->n, c.num_channels, {{h->finalb, c.dim}}, h->to_pred_w);
   d.epi = E2B_EPI_F32; d.bias = h->to_pred_b; d.out = pred; d.ldo = c.num_channels;
   CK(e2b_gemm_launch(&d, st));
   return 0;
@@ -444,16 +531,22 @@ int set_ctx(e2b_handle* h, const float* ctx_dev, const int* ctx_lens_host, cudaS
     if (cl[b] < 0 || cl[b] > h->nc) return fail(h, "ctx_lens[%d]=%d outside [0,%d]", b, cl[b], h->nc);
   }
   CU(cudaMemcpyAsync(h->ctx_lens_dev, cl.data(), h->B * sizeof(int), cudaMemcpyHostToDevice, st));
-  CK(e2b_cast_pad_launch(ctx_dev, c.dim, h->ctxb, c.dim, h->B * h->nc, c.dim, st));
+  if (cast_act(h, ctx_dev, c.dim, h->ctxb, c.dim, c.dim, (size_t)h->B * h->nc, st)) return -1;
   for (int l = 0; l < c.depth; ++l) {
     // k2 = rope(to_k(ctx)) at positions N-nc..N-1 (x-transformers uses the LAST nc rows of the table), v2 = to_v(ctx)
-    e2b_gemm_desc d = gd((size_t)h->B * h->nc, 2 * h->HD, c.dim, h->ctxb, c.dim, h->L[l].kv2_w);
+    e2b_gemm_desc d = gdesc(h, (size_t)h->B * h->nc, 2 * h->HD, {{h->ctxb, c.dim}}, h->L[l].kv2_w);
     d.epi = E2B_EPI_QKV;
-    d.out = h->k2[l]; d.ldo = h->HD;
+    d.ldo = h->HD;
     d.q_end = 0; d.k_end = h->HD; d.v_end = 2 * h->HD;
     d.q_scale = 1.0f;
     d.rope = h->rope; d.pos_off = h->N - h->nc; d.rows_per_batch = h->nc;
-    d.vt = h->vt2[l]; d.vt_ld = h->ncpad; d.heads_v = c.heads;
+    d.heads_v = c.heads;
+    if (!h->f32) {
+      d.out = h->k2[l];
+      d.vt = h->vt2[l]; d.vt_ld = h->ncpad;
+    } else {
+      d.out = h->k2f[l]; d.qk_f32 = h->k2f[l]; d.v_f32 = h->v2f[l]; d.v_f32_ld = h->HD;
+    }
     CK(e2b_gemm_launch(&d, st));
   }
   CU(cudaStreamSynchronize(st));   // cl (host vector) must outlive the async copy
@@ -485,6 +578,7 @@ extern "C" int e2b_create(const e2b_config* cfg, e2b_handle** out) {
   if (cfg->dim % 64 || cfg->dim_text % 64 || cfg->dim_frames % 64 || cfg->num_channels % 64)
     return fail(h, "e2b_create: dim/dim_text/dim_frames/num_channels must be multiples of 64");
   if (cfg->notes <= 0 || cfg->notes > 64) return fail(h, "e2b_create: notes must be in (0,64]");
+  if (cfg->precision != 0 && cfg->precision != 1) return fail(h, "e2b_create: precision must be 0 (bf16) or 1 (error-compensated fp32)");
   if (cfg->kernel_size != 31) return fail(h, "e2b_create: kernel_size must be 31");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(h, "e2b_create: no CUDA device (this library has no CPU path)");
@@ -493,6 +587,7 @@ extern "C" int e2b_create(const e2b_config* cfg, e2b_handle** out) {
   h->HD = cfg->heads * 64; h->HDt = cfg->heads * 64; h->HDf = cfg->frames_heads * 64;
   h->inner = cfg->dim * cfg->ff_mult; h->inner_t = cfg->dim_text * cfg->ff_mult; h->inner_f = cfg->dim_frames * cfg->ff_mult;
   h->nmat = cfg->depth * 6;
+  h->f32 = cfg->precision == 1;
   *out = h;
   return 0;
 }
@@ -529,7 +624,7 @@ extern "C" int e2b_load_weights(e2b_handle* h, const e2b_tensor* tensors, int n,
   if (copy_f32(h, w, "proj_in.bias", &h->proj_in_b, dim, -1, st)) return -1;
   if (pack_linear(h, w, "to_pred.weight", &h->to_pred_w, c.num_channels, dim, st)) return -1;
   if (copy_f32(h, w, "to_pred.bias", &h->to_pred_b, c.num_channels, -1, st)) return -1;
-  if (pack_linear(h, w, "proj_frames.weight", &h->pf_w, df, c.notes, st, 64)) return -1;   // K padded 51 -> 64 with zeros
+  if (pack_linear(h, w, "proj_frames.weight", &h->pf_w, df, c.notes, st, {{c.notes, 64}})) return -1;   // K padded 51 -> 64 with zeros
   if (copy_f32(h, w, "proj_frames.bias", &h->pf_b, df, -1, st)) return -1;
 
   // RoPE table from the (shared) inv_freq buffer: cos/sin(pos * inv_freq[j]) in fp32 like the reference
@@ -558,7 +653,7 @@ extern "C" int e2b_load_weights(e2b_handle* h, const e2b_tensor* tensors, int n,
     const std::string a = T + "layers." + std::to_string(l) + ".0.";
     const std::string x = T + "layers." + std::to_string(l) + ".1.";
     const std::string f = T + "layers." + std::to_string(l) + ".2.";
-    if (l >= c.depth / 2 && pack_linear(h, w, a + "0.weight", &Lw.skip_w, dim, 2 * dim, st)) return -1;
+    if (l >= c.depth / 2 && pack_linear(h, w, a + "0.weight", &Lw.skip_w, dim, 2 * dim, st, {{dim, dim}, {dim, dim}})) return -1;
     if (pack_conv(h, w, a + "1", dim, &Lw.conv_w, &Lw.conv_b, st)) return -1;
     if (pack_concat(h, w, {{a + "3.to_q.weight", HD}, {a + "3.to_k.weight", HD}, {a + "3.to_v.weight", HD}, {a + "3.to_v_head_gate.weight", H}}, dim,
                     &Lw.qkv_w, st)) return -1;
@@ -582,10 +677,10 @@ extern "C" int e2b_load_weights(e2b_handle* h, const e2b_tensor* tensors, int n,
     }
     if (pack_stream(h, w, x, dt, H, h->inner_t, Lw.t, st)) return -1;
     if (pack_stream(h, w, f, df, c.frames_heads, h->inner_f, Lw.f, st)) return -1;
-    if (pack_linear(h, w, x + "5.text_frames_to_audio.weight", &Lw.tfa_w, dim, dim + dt + df, st)) return -1;
+    if (pack_linear(h, w, x + "5.text_frames_to_audio.weight", &Lw.tfa_w, dim, dim + dt + df, st, {{dim, dim}, {dt, dt}, {df, df}})) return -1;
     if (l < c.depth - 1) {
-      if (pack_linear(h, w, x + "5.audio_to_text.weight", &Lw.at_w, dt, dim + dt, st)) return -1;
-      if (pack_linear(h, w, x + "5.audio_to_frames.weight", &Lw.af_w, df, dim + df, st)) return -1;
+      if (pack_linear(h, w, x + "5.audio_to_text.weight", &Lw.at_w, dt, dim + dt, st, {{dim, dim}, {dt, dt}})) return -1;
+      if (pack_linear(h, w, x + "5.audio_to_frames.weight", &Lw.af_w, df, dim + df, st, {{dim, dim}, {df, df}})) return -1;
     }
   }
   DA(h->wallocs, h->tm_w, h->nmat);
@@ -620,27 +715,39 @@ extern "C" int e2b_prepare(e2b_handle* h, int B, int n, int nc, int P) {
     DA(h->sallocs, h->text[i], M * dt);
     DA(h->sallocs, h->frames[i], M * df);
   }
-  DA(h->sallocs, h->xb, M * dim);
-  DA(h->sallocs, h->textb, M * dt);
-  DA(h->sallocs, h->framesb, M * df);
-  DA(h->sallocs, h->xtmpb, M * dim);
+  const size_t w2 = h->f32 ? 2 : 1;      // bf16 A operands are (hi, lo) pairs in the error-compensated mode
+  DA(h->sallocs, h->xb, M * dim * w2);
+  DA(h->sallocs, h->textb, M * dt * w2);
+  DA(h->sallocs, h->framesb, M * df * w2);
+  DA(h->sallocs, h->xtmpb, M * dim * w2);
   h->skipb.resize(c.depth / 2);
-  for (auto& p : h->skipb) DA(h->sallocs, p, M * dim);
-  DA(h->sallocs, h->nb, M * Cmax);
-  DA(h->sallocs, h->qk, M * 2 * HDmax);
-  DA(h->sallocs, h->vt, (size_t)h->Bt * Hmax * 64 * h->Npad);
+  for (auto& p : h->skipb) DA(h->sallocs, p, M * dim * w2);
+  DA(h->sallocs, h->nb, M * Cmax * w2);
   DA(h->sallocs, h->hg, M * Hmax);
-  DA(h->sallocs, h->ob, M * HDmax);
-  DA(h->sallocs, h->hb, M * inner_max);
-  DA(h->sallocs, h->ybf, (size_t)h->Bt * n * c.num_channels);
-  DA(h->sallocs, h->finalb, (size_t)h->Bt * n * dim);
-  DA(h->sallocs, h->fin, (size_t)h->Bt * n * 64);
-  DA(h->sallocs, h->ctxb, (size_t)B * nc * dim);
-  h->k2.resize(c.depth);
-  h->vt2.resize(c.depth);
-  for (int l = 0; l < c.depth; ++l) {
-    DA(h->sallocs, h->k2[l], (size_t)B * nc * h->HD);
-    DA(h->sallocs, h->vt2[l], (size_t)B * c.heads * 64 * h->ncpad);
+  DA(h->sallocs, h->ob, M * HDmax * w2);
+  DA(h->sallocs, h->hb, M * inner_max * w2);
+  DA(h->sallocs, h->ybf, (size_t)h->Bt * n * c.num_channels * w2);
+  DA(h->sallocs, h->finalb, (size_t)h->Bt * n * dim * w2);
+  DA(h->sallocs, h->fin, (size_t)h->Bt * n * 64 * w2);
+  DA(h->sallocs, h->ctxb, (size_t)B * nc * dim * w2);
+  if (!h->f32) {
+    DA(h->sallocs, h->qk, M * 2 * HDmax);
+    DA(h->sallocs, h->vt, (size_t)h->Bt * Hmax * 64 * h->Npad);
+    h->k2.resize(c.depth);
+    h->vt2.resize(c.depth);
+    for (int l = 0; l < c.depth; ++l) {
+      DA(h->sallocs, h->k2[l], (size_t)B * nc * h->HD);
+      DA(h->sallocs, h->vt2[l], (size_t)B * c.heads * 64 * h->ncpad);
+    }
+  } else {
+    DA(h->sallocs, h->qkf, M * 2 * HDmax);
+    DA(h->sallocs, h->vf, M * HDmax);
+    h->k2f.resize(c.depth);
+    h->v2f.resize(c.depth);
+    for (int l = 0; l < c.depth; ++l) {
+      DA(h->sallocs, h->k2f[l], (size_t)B * nc * h->HD);
+      DA(h->sallocs, h->v2f[l], (size_t)B * nc * h->HD);
+    }
   }
   DA(h->sallocs, h->fr0, M * df);
   DA(h->sallocs, h->clip, (size_t)B * n * dt);
@@ -687,13 +794,16 @@ extern "C" int e2b_set_conditions(e2b_handle* h, const float* clip_dev, const fl
   // piano-roll stream: proj_frames (K padded to 64) + registers, per pass (roll dropped => proj_frames(0) = bias)
   const size_t per_pass = (size_t)h->B * h->n;
   for (int p = 0; p < h->P; ++p) {
-    bf16* dst = h->fin + p * per_pass * 64;
-    if (roll_dev && !(h->pass_flags[p] & E2B_DROP_ROLL)) CK(e2b_cast_pad_launch(roll_dev, c.notes, dst, 64, (int)per_pass, c.notes, st));
-    else CU(cudaMemsetAsync(dst, 0, per_pass * 64 * sizeof(bf16), st));
+    bf16* dst = h->fin + p * per_pass * ldb(h, 64);
+    if (roll_dev && !(h->pass_flags[p] & E2B_DROP_ROLL)) {
+      if (cast_act(h, roll_dev, c.notes, dst, c.notes, 64, per_pass, st)) return -1;
+    } else {
+      CU(cudaMemsetAsync(dst, 0, per_pass * ldb(h, 64) * sizeof(bf16), st));
+    }
   }
   CK(e2b_init_stream_launch(h->fr0, nullptr, h->f_registers, nullptr, -1, nullptr, nullptr, h->Bt, h->n, R, c.dim_frames, st));
   {
-    e2b_gemm_desc d = gd((size_t)h->Bt * h->n, c.dim_frames, 64, h->fin, 64, h->pf_w);
+    e2b_gemm_desc d = gdesc(h, (size_t)h->Bt * h->n, c.dim_frames, {{h->fin, 64}}, h->pf_w);
     d.epi = E2B_EPI_F32; d.bias = h->pf_b;
     d.out = h->fr0; d.ldo = c.dim_frames;
     d.rpb_in = h->n; d.rpb_out = h->N; d.row_off = R;
@@ -713,7 +823,7 @@ extern "C" int e2b_forward(e2b_handle* h, const float* x_dev, float t, float* pr
   if (compute_time_tables(h, &t, 1, st)) return -1;
   CU(cudaStreamSynchronize(st));   // &t is a stack address
   for (int p = 0; p < h->P; ++p)
-    CK(e2b_cast_pad_launch(x_dev, c.num_channels, h->ybf + p * per_pass * c.num_channels, c.num_channels, (int)per_pass, c.num_channels, st));
+    if (cast_act(h, x_dev, c.num_channels, h->ybf + p * per_pass * ldb(h, c.num_channels), c.num_channels, c.num_channels, per_pass, st)) return -1;
   if (init_streams_from_state(h, st)) return -1;
   if (forward_core(h, GamRef{h->gam, 0}, st)) return -1;
   return pred_head(h, pred_dev, st);
@@ -733,14 +843,19 @@ extern "C" int e2b_sample(e2b_handle* h, float* y_dev, const float* t_grid_host,
   if (steps == 1) return 0;
   if (compute_time_tables(h, t_grid_host, steps - 1, st)) return -1;
   for (int p = 0; p < h->P; ++p)
-    CK(e2b_cast_pad_launch(y_dev, c.num_channels, h->ybf + p * per_pass * c.num_channels, c.num_channels, (int)per_pass, c.num_channels, st));
+    if (cast_act(h, y_dev, c.num_channels, h->ybf + p * per_pass * ldb(h, c.num_channels), c.num_channels, c.num_channels, per_pass, st)) return -1;
   for (int s = 0; s < steps - 1; ++s) {
     const float dt = t_grid_host[s + 1] - t_grid_host[s];
     if (init_streams_from_state(h, st)) return -1;
     if (forward_core(h, GamRef{h->gam + (size_t)s * h->nmat * c.dim, 0}, st)) return -1;
     if (pred_head(h, h->pred, st)) return -1;
-    CK(e2b_guided_euler_launch(y_dev, h->pred, h->P, h->B, per_sample, guidance_w_host, dt, apg, keep_parallel, h->apg_scratch, h->ybf,
-                               h->P, st));
+    // bf16 mode: the Euler kernel also emits the bf16 copies of y that feed the next proj_in; the error-compensated mode
+    // needs (hi, lo) pairs, produced by a separate split cast
+    CK(e2b_guided_euler_launch(y_dev, h->pred, h->P, h->B, per_sample, guidance_w_host, dt, apg, keep_parallel, h->apg_scratch,
+                               h->f32 ? nullptr : h->ybf, h->f32 ? 0 : h->P, st));
+    if (h->f32 && s + 1 < steps - 1)
+      for (int p = 0; p < h->P; ++p)
+        if (cast_act(h, y_dev, c.num_channels, h->ybf + p * per_pass * ldb(h, c.num_channels), c.num_channels, c.num_channels, per_pass, st)) return -1;
   }
   return 0;
 }
@@ -759,7 +874,8 @@ extern "C" int e2b_transformer_forward(e2b_handle* h, const float* x_dev, const 
   if (set_lens(h, lens_host, st)) return -1;
   if (set_ctx(h, ctx_dev, ctx_lens_host, st)) return -1;
   if (compute_time_tables(h, times_host, h->B, st)) return -1;
-  CK(e2b_init_stream_launch(h->x[0], h->xb, h->registers, x_dev, h->B, nullptr, h->abs_pos, h->B, h->n, R, c.dim, st));
+  CK(e2b_init_stream_split_launch(h->x[0], h->xb, ldb(h, c.dim), spl(h, c.dim), h->registers, x_dev, h->B, nullptr, h->abs_pos, h->B, h->n, R,
+                                  c.dim, st));
   CK(e2b_init_stream_launch(h->text[0], nullptr, h->t_registers, text_dev, h->B, nullptr, nullptr, h->B, h->n, R, c.dim_text, st));
   CK(e2b_init_stream_launch(h->frames[0], nullptr, h->f_registers, frames_dev, h->B, nullptr, nullptr, h->B, h->n, R, c.dim_frames, st));
   if (forward_core(h, GamRef{h->gam, h->nmat * c.dim}, st)) return -1;

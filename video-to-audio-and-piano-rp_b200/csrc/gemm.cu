@@ -25,9 +25,9 @@ constexpr int BK = 64;
 constexpr int GEMM_THREADS = 256;
 
 struct GemmArgs {
-  CUtensorMap tmA[3];
+  CUtensorMap tmA[E2B_MAX_SRC];
   CUtensorMap tmB;
-  int kb_end[3];
+  int kb_end[E2B_MAX_SRC];
   e2b_gemm_desc d;
 };
 
@@ -69,6 +69,17 @@ constexpr int EPI_PITCH4 = 9;                         // float4 per staged row (
 constexpr int EPI_BUF_BYTES = 32 * EPI_PITCH4 * 16;   // per epilogue warp
 
 __device__ __forceinline__ uint2 pack4_bf16(const float4& v) { return make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)); }
+// bf16 store of 4 values; split > 0 also stores the rounding residual lo = bf16(v - hi) `split` elements further (the
+// error-compensated fp32 mode: consumers read (hi, lo, hi) against weights (W_hi, W_hi, W_lo))
+__device__ __forceinline__ void st_bf16x4(char* p, const float4& v, int split) {
+  const uint2 hi = pack4_bf16(v);
+  *reinterpret_cast<uint2*>(p) = hi;
+  if (split > 0) {
+    const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&hi.x), h1 = *reinterpret_cast<const __nv_bfloat162*>(&hi.y);
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    *reinterpret_cast<uint2*>(p + 2 * split) = make_uint2(pack_bf16(v.x - f0.x, v.y - f0.y), pack_bf16(v.z - f1.x, v.w - f1.y));
+  }
+}
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float4 f4_one() { return make_float4(1.f, 1.f, 1.f, 1.f); }
 
@@ -264,7 +275,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             o.y = (a.y + bv.y) * gelu_erf(gt[k].y + bg.y);
             o.z = (a.z + bv.z) * gelu_erf(gt[k].z + bg.z);
             o.w = (a.w + bv.w) * gelu_erf(gt[k].w + bg.w);
-            if (R.out[k]) *reinterpret_cast<uint2*>(R.out[k] + ob) = pack4_bf16(o);
+            if (R.out[k]) st_bf16x4(R.out[k] + ob, o, d.split);
           }
           __syncwarp();
         }
@@ -283,7 +294,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
-          if (col0 >= d.k_end && col0 < d.v_end) {
+          if (col0 >= d.k_end && col0 < d.v_end && d.v_f32 == nullptr) {
             // V^T store: thread = key position, so the 32 lanes of a store are 32 consecutive keys (64 contiguous bytes)
             const int row = m0 + ew * 32 + lane;
             if (row < d.M) {
@@ -308,8 +319,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
               o.y = (a.y * cs[k].x + a.x * cs[k].y) * sc;
               o.z = (a.z * cs[k].z - a.w * cs[k].w) * sc;
               o.w = (a.w * cs[k].z + a.z * cs[k].w) * sc;
-              if (R.out[k]) *reinterpret_cast<uint2*>(R.out[k] + col * 2) = pack4_bf16(o);
+              if (R.out[k]) {
+                if (d.qk_f32) *reinterpret_cast<float4*>(d.qk_f32 + (size_t)(m0 + ew * 32 + 4 * k + rsub) * d.ldo + col) = o;
+                else *reinterpret_cast<uint2*>(R.out[k] + col * 2) = pack4_bf16(o);
+              }
             }
+          } else if (col0 < d.v_end) {               // fp32 mode: v as plain fp32 [M, v_f32_ld]
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (R.out[k]) *reinterpret_cast<float4*>(d.v_f32 + (size_t)(m0 + ew * 32 + 4 * k + rsub) * d.v_f32_ld + (col - d.k_end)) = bufr[4 * k * EPI_PITCH4];
           } else if (col < d.N) {                    // head-gate columns [v_end, N): few, scalar stores
             const int gc = col - d.v_end;
 #pragma unroll
@@ -361,12 +379,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
               const float4 a = bufr[4 * k * EPI_PITCH4];
               if constexpr (EPI == E2B_EPI_BF16) {
                 const float4 o = make_float4(a.x + bias4.x, a.y + bias4.y, a.z + bias4.z, a.w + bias4.w);
-                if (R.out[k]) *reinterpret_cast<uint2*>(R.out[k] + lc * 2) = pack4_bf16(o);
+                if (R.out[k]) st_bf16x4(R.out[k] + lc * 2, o, d.split);
               } else if constexpr (EPI == E2B_EPI_F32) {
                 const float4 o = make_float4(a.x + bias4.x + pre[k].x, a.y + bias4.y + pre[k].y, a.z + bias4.z + pre[k].z, a.w + bias4.w + pre[k].w);
                 if (R.out[k]) {
                   *reinterpret_cast<float4*>(R.out[k] + lc * 4) = o;
-                  if (R.out2[k]) *reinterpret_cast<uint2*>(R.out2[k] + lc * 2) = pack4_bf16(o);
+                  if (R.out2[k]) st_bf16x4(R.out2[k] + lc * 2, o, d.split);
                 }
               } else {   // RESID
                 float4 gg = gate4;
@@ -380,7 +398,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                 }
                 if (R.out[k]) {
                   *reinterpret_cast<float4*>(R.out[k] + lc * 4) = r;
-                  if (R.out2[k]) *reinterpret_cast<uint2*>(R.out2[k] + lc * 2) = pack4_bf16(r);
+                  if (R.out2[k]) st_bf16x4(R.out2[k] + lc * 2, r, d.split);
                 }
               }
             }
@@ -514,12 +532,12 @@ extern "C" const char* e2b_kernel_last_error(void) { return g_err; }
 
 extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
   if (d->M <= 0 || d->N <= 0) return 0;
-  if (d->num_src < 1 || d->num_src > 3) { e2b_set_kernel_error("gemm: num_src %d", d->num_src); return -1; }
+  if (d->num_src < 1 || d->num_src > E2B_MAX_SRC) { e2b_set_kernel_error("gemm: num_src %d", d->num_src); return -1; }
   GemmArgs a;
   memset(&a, 0, sizeof(a));
   a.d = *d;
   int k = 0;
-  for (int s = 0; s < 3; ++s) {
+  for (int s = 0; s < E2B_MAX_SRC; ++s) {
     if (s < d->num_src) {
       if (d->ka[s] <= 0 || d->ka[s] % BK) { e2b_set_kernel_error("gemm: ka[%d]=%d must be a positive multiple of 64", s, d->ka[s]); return -1; }
       if (make_tmap_bf16(&a.tmA[s], d->a[s], d->M, d->ka[s], d->lda[s], BM)) return -1;

@@ -13,13 +13,14 @@ extern "C" {
 // GEMM  C[M,N] = A[M,K] * W[N,K]^T  (bf16 x bf16 -> fp32 in TMEM), A given as up to 3 K-concatenated sources.
 // ---------------------------------------------------------------------------------------------------------------
 enum { E2B_EPI_BF16 = 0, E2B_EPI_F32 = 1, E2B_EPI_GEGLU = 2, E2B_EPI_RESID = 3, E2B_EPI_QKV = 4 };
+enum { E2B_MAX_SRC = 9 };
 
 typedef struct e2b_gemm_desc {
   int M, N, K;               // K = sum of ka[]; every ka[] a multiple of 64; N = rows of W
-  int num_src;
-  const void* a[3];          // bf16 row-major sources [M, ka[s]] with leading dimension lda[s] (elements)
-  int lda[3];
-  int ka[3];
+  int num_src;               // up to E2B_MAX_SRC (3 logical sources x (hi, lo, hi) in the error-compensated fp32 mode)
+  const void* a[9];          // bf16 row-major sources [M, ka[s]] with leading dimension lda[s] (elements)
+  int lda[9];
+  int ka[9];
   const void* w;             // bf16 [N, K] row-major (torch nn.Linear layout), leading dimension ldw
   int ldw;
   int epi;                   // E2B_EPI_*
@@ -50,6 +51,13 @@ typedef struct e2b_gemm_desc {
   float* hgate;              // fp32 [M, hgate_ld] = sigmoid(acc + hgate_bias)
   int hgate_ld;
   const float* hgate_bias;
+  // Error-compensated ("fp32") mode.  split > 0: every bf16 output v is stored as the pair hi = bf16(v) at column c and
+  // lo = bf16(v - hi) at column c + split (EPI_BF16 / EPI_GEGLU `out`; EPI_F32 / EPI_RESID `out_b16`).
+  int split;
+  // EPI_QKV in fp32 mode: q,k (RoPE'd, scaled) go to qk_f32 [M, ldo] and v to v_f32 [M, v_f32_ld] instead of bf16 out / vt.
+  float* qk_f32;
+  float* v_f32;
+  int v_f32_ld;
 } e2b_gemm_desc;
 
 int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream);
@@ -77,14 +85,30 @@ typedef struct e2b_attn_desc {
 
 int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream);
 
+// Exact fp32 attention for the error-compensated mode (SIMT, one warp per query row): q,k,v fp32 row-major with head h at
+// columns [col0 + h*64, +64); same masking / gating semantics; out is a bf16 (hi, lo) pair when out_split > 0.
+typedef struct e2b_attn_f32_desc {
+  int batch, heads, q_rows_per_batch, kv_rows_per_batch;
+  const float* q; int ldq; int q_col0;
+  const float* k; int ldk; int k_col0;
+  const float* v; int ldv; int v_col0;
+  int kv_batch_mod;
+  const int* kv_lens; int kv_lens_add;
+  const float* hgate; int hgate_ld;
+  void* out; int ldo; int out_split;
+  float softclamp;
+} e2b_attn_f32_desc;
+int e2b_attention_f32_launch(const e2b_attn_f32_desc* d, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------------------------------
 // element-wise / warp-level kernels (elementwise.cu)
 // ---------------------------------------------------------------------------------------------------------------
 // y[r_out,:] = x[r,:] / max(||x[r]||, 1e-12) * sqrt(C) * scale[b(r), :]     (scale = g, or gamma+1 per batch)
 // rows_per_batch/skip_rows: r = b*rows_per_batch + skip_rows + i  ->  r_out = b*(rows_per_batch-skip_rows) + i
 // y is bf16 unless out_f32 != 0
+// out_mode: 0 = bf16, 1 = fp32, 2 = bf16 (hi, lo) pair with lo at column + C (ldy must be >= 2C)
 int e2b_rmsnorm_launch(const float* x, int ldx, void* y, int ldy, const float* scale, int scale_bstride, int batch,
-                       int rows_per_batch, int skip_rows, int C, int out_f32, cudaStream_t stream);
+                       int rows_per_batch, int skip_rows, int C, int out_mode, cudaStream_t stream);
 
 // y = x + mask * silu(dwconv31(mask * x) + bias) over the sequence axis, channels-last [batch, N, C]; w is [K, C]
 int e2b_dwconv_launch(const float* x, float* y, const float* w /*[K,C] (transposed conv weight)*/, const float* bias, const int* lens,
@@ -99,13 +123,20 @@ int e2b_time_gemv_launch(const float* tcond, int nt, int dim, const float* const
 
 // stream init: dst[b, 0:R, :] = registers ; dst[b, R+i, :] = src[b % src_batches, i, :] + add_table[i, :]
 // (0 when src == NULL or drop[b]); src_batches < 0 => write the register rows only.  Optional bf16 copy.
+// dst_b16 has leading dimension ldb (0 => C); b16_split > 0 stores the (hi, lo) pair with lo at column + b16_split.
 int e2b_init_stream_launch(float* dst, void* dst_b16, const float* registers, const float* src, int src_batches,
                            const unsigned char* drop, const float* add_table, int batch, int n, int R, int C,
                            cudaStream_t stream);
+int e2b_init_stream_split_launch(float* dst, void* dst_b16, int ldb, int b16_split, const float* registers, const float* src,
+                                 int src_batches, const unsigned char* drop, const float* add_table, int batch, int n, int R, int C,
+                                 cudaStream_t stream);
 int e2b_transpose_launch(const float* src, float* dst, int rows, int cols, cudaStream_t stream);
 
 // fp32 -> bf16 cast with column padding: dst[r, 0:C] = src[r, 0:C], dst[r, C:ldd] = 0
 int e2b_cast_pad_launch(const float* src, int lds, void* dst, int ldd, int rows, int C, cudaStream_t stream);
+// dst[r, 0:W] for r < rows: part 0 => bf16(src) ("hi"), part 1 => bf16(src - hi) ("lo"); columns C..W are zero.  No padding
+// beyond W is written (dst may be a column block of a wider matrix with leading dimension ldd).
+int e2b_cast_part_launch(const float* src, int lds, void* dst, int ldd, int rows, int C, int W, int part, cudaStream_t stream);
 
 // guided Euler step.  pred: [P, B, n, d] fp32 (pass 0 = full conditioning, passes 1..P-1 the dropped ones)
 //   v = pred0 + sum_k w[k] * (pred0 - pred_k) ; y += dt * v ; optional bf16 copies of the new y for P passes

@@ -14,7 +14,7 @@ DROP_CLIP, DROP_CTX, DROP_ROLL = 1, 2, 4
 
 class Config(C.Structure):
     _fields_ = [(k, C.c_int) for k in ('depth', 'dim', 'dim_text', 'dim_frames', 'heads', 'dim_head', 'frames_heads',
-                                       'num_channels', 'num_registers', 'kernel_size', 'notes', 'max_seq_len', 'ff_mult')]
+                                       'num_channels', 'num_registers', 'kernel_size', 'notes', 'max_seq_len', 'ff_mult', 'precision')]
 
 
 class Tensor(C.Structure):
@@ -24,7 +24,7 @@ class Tensor(C.Structure):
 class GemmDesc(C.Structure):
     _fields_ = [
         ('M', C.c_int), ('N', C.c_int), ('K', C.c_int), ('num_src', C.c_int),
-        ('a', C.c_void_p * 3), ('lda', C.c_int * 3), ('ka', C.c_int * 3),
+        ('a', C.c_void_p * 9), ('lda', C.c_int * 9), ('ka', C.c_int * 9),
         ('w', C.c_void_p), ('ldw', C.c_int), ('epi', C.c_int),
         ('bias', C.c_void_p), ('out', C.c_void_p), ('ldo', C.c_int),
         ('out_b16', C.c_void_p), ('ldo_b16', C.c_int),
@@ -37,6 +37,7 @@ class GemmDesc(C.Structure):
         ('rope', C.c_void_p), ('pos_off', C.c_int),
         ('vt', C.c_void_p), ('vt_ld', C.c_int), ('heads_v', C.c_int),
         ('hgate', C.c_void_p), ('hgate_ld', C.c_int), ('hgate_bias', C.c_void_p),
+        ('split', C.c_int), ('qk_f32', C.c_void_p), ('v_f32', C.c_void_p), ('v_f32_ld', C.c_int),
     ]
 
 
@@ -52,7 +53,20 @@ class AttnDesc(C.Structure):
     ]
 
 
+class AttnF32Desc(C.Structure):
+    _fields_ = [
+        ('batch', C.c_int), ('heads', C.c_int), ('q_rows_per_batch', C.c_int), ('kv_rows_per_batch', C.c_int),
+        ('q', C.c_void_p), ('ldq', C.c_int), ('q_col0', C.c_int),
+        ('k', C.c_void_p), ('ldk', C.c_int), ('k_col0', C.c_int),
+        ('v', C.c_void_p), ('ldv', C.c_int), ('v_col0', C.c_int),
+        ('kv_batch_mod', C.c_int), ('kv_lens', C.c_void_p), ('kv_lens_add', C.c_int),
+        ('hgate', C.c_void_p), ('hgate_ld', C.c_int),
+        ('out', C.c_void_p), ('ldo', C.c_int), ('out_split', C.c_int), ('softclamp', C.c_float),
+    ]
+
+
 EPI_BF16, EPI_F32, EPI_GEGLU, EPI_RESID, EPI_QKV = range(5)
+PRECISIONS = {'bf16': 0, 'fp32': 1}
 
 _SIGS = {
     # include/e2b.h
@@ -77,6 +91,7 @@ _SIGS = {
     # kernel-level entry points (csrc/kernels.h) used by the unit tests
     'e2b_gemm_launch': (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
     'e2b_attention_launch': (C.c_int, [C.POINTER(AttnDesc), C.c_void_p]),
+    'e2b_attention_f32_launch': (C.c_int, [C.POINTER(AttnF32Desc), C.c_void_p]),
     'e2b_rmsnorm_launch': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_void_p]),
     'e2b_dwconv_launch': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
@@ -87,6 +102,7 @@ _SIGS = {
     'e2b_init_stream_launch': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'e2b_cast_pad_launch': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'e2b_cast_part_launch': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'e2b_guided_euler_launch': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.POINTER(C.c_float),
                                           C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'e2b_kernel_last_error': (C.c_char_p, []),

@@ -283,8 +283,10 @@ class Transformer(Module):
         self._engine = None
 
     # ---- engine management -------------------------------------------------------------------------------
-    def engine_config(self, num_channels=64):
-        return dict(depth=self.depth, dim=self.dim, dim_text=self.dim_text, dim_frames=self.dim_frames, heads=self.heads,
+    precision = 'bf16'      # 'bf16' (tensor-core path, rel-L2 <= 1e-2) or 'fp32' (error-compensated mode, <= 1e-4)
+
+    def engine_config(self, num_channels=64, precision=None):
+        return dict(precision=_lib.PRECISIONS[precision or self.precision], depth=self.depth, dim=self.dim, dim_text=self.dim_text, dim_frames=self.dim_frames, heads=self.heads,
                     dim_head=self.dim_head, frames_heads=self.frames_heads, num_channels=num_channels,
                     num_registers=self.num_registers, kernel_size=self.kernel_size, notes=NOTES, max_seq_len=self.max_seq_len,
                     ff_mult=self.ff_mult)
@@ -298,6 +300,8 @@ class Transformer(Module):
         return super().load_state_dict(*a, **k)
 
     def _standalone_engine(self):
+        if self._engine is not None and getattr(self, '_engine_precision', None) != self.precision:
+            self._engine = None
         if self._engine is None:
             dev = self.registers.device
             tensors = _named_tensors(self, 'transformer.')
@@ -305,6 +309,7 @@ class Transformer(Module):
             tensors.update({'proj_in.weight': z(self.dim, 64), 'proj_in.bias': z(self.dim), 'to_pred.weight': z(64, self.dim),
                             'to_pred.bias': z(64), 'proj_frames.weight': z(self.dim_frames, NOTES), 'proj_frames.bias': z(self.dim_frames)})
             self._engine = _Engine(self.engine_config(64), tensors, dev)
+            self._engine_precision = self.precision
         return self._engine
 
     @torch.no_grad()
@@ -486,14 +491,19 @@ class E2TTS(Module):
         self._engine = None
         return super().load_state_dict(state_dict, strict=strict, **k)
 
+    precision = 'bf16'      # set to 'fp32' for the error-compensated mode (rel-L2 <= 1e-4 vs the fp32 reference)
+
     def engine(self) -> _Engine:
-        """Repack the current parameters into libe2b (done once per load / device move)."""
+        """Repack the current parameters into libe2b (done once per load / device move / precision change)."""
+        if self._engine is not None and self._engine_precision != self.precision:
+            self._engine = None
         if self._engine is None:
             tensors = _named_tensors(self.transformer, 'transformer.')
             for name in ('proj_in', 'to_pred', 'proj_frames'):
                 m = getattr(self, name)
                 tensors[name + '.weight'], tensors[name + '.bias'] = m.weight, m.bias
-            self._engine = _Engine(self.transformer.engine_config(self.num_channels), tensors, self.device)
+            self._engine = _Engine(self.transformer.engine_config(self.num_channels, self.precision), tensors, self.device)
+            self._engine_precision = self.precision
         return self._engine
 
     # ---- condition encoders (outside the hot path) -------------------------------------------------------
