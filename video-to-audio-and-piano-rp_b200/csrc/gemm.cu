@@ -22,7 +22,6 @@ namespace e2b {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 256;
 
 struct GemmArgs {
   CUtensorMap tmA[E2B_MAX_SRC];
@@ -31,13 +30,17 @@ struct GemmArgs {
   e2b_gemm_desc d;
 };
 
-template <int BN>
+// EW = number of epilogue warps.  4: one per TMEM lane quarter, 4-stage operand ring (large K, MMA-bound).  8: two per
+// quarter taking alternate 32-column chunks, 3-stage ring: for K <= 1024 the epilogue (one warp per scheduler, IPC ~0.3)
+// is longer than the 8K-cycle mainloop of a tile, so thread-level parallelism in the epilogue is worth a pipeline stage.
+template <int BN, int EW>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * 4608 /*epilogue transpose buffers*/ + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGES = (BN == 256) ? (EW == 8 ? 3 : 4) : 6;
+  static constexpr int THREADS = 128 + 32 * EW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EW * 4608 /*epilogue transpose buffers*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;   // 512 or 256: both powers of two
 };
 
@@ -99,9 +102,9 @@ struct EpiRows {
   bool valid[8];         // EPI_RESID row mask (valid length)
 };
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmArgs args) {
-  using Cfg = GemmCfg<BN>;
+template <int BN, int EPI, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_constant__ GemmArgs args) {
+  using Cfg = GemmCfg<BN, EW>;
   // Used directly (no integer round-trip) so the compiler keeps the shared address space: the earlier manual 1024-byte
   // round-up through uintptr_t turned every access into generic LD.E/ST.E.  SWIZZLE_128B needs a 1024-byte aligned base;
   // with no static shared memory the dynamic window starts at offset 0 -- checked once below.
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
   uint8_t* sEpi = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 4 * EPI_BUF_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + EW * EPI_BUF_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::STAGES;
   uint64_t* tfull = bars + 2 * Cfg::STAGES;
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 128);
+      mbar_init(&tempty[s], 32 * EW);
     }
     fence_mbar_init();
   }
@@ -194,8 +197,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (TMEM -> regs -> smem transpose -> global)
-    const int ew = warp - 4;   // == warp % 4: the TMEM lane quarter this warp may read
-    float4* buf = reinterpret_cast<float4*>(sEpi + ew * EPI_BUF_BYTES);
+    const int ewi = warp - 4;
+    const int ew = ewi & 3;    // == warp % 4: the TMEM lane quarter this warp may read
+    const int cw = ewi >> 2;   // with 8 epilogue warps: which alternate 32-column chunks this warp takes
+    constexpr int CSTEP = EW / 4;
+    float4* buf = reinterpret_cast<float4*>(sEpi + ewi * EPI_BUF_BYTES);
     const int rsub = lane >> 3, cg = lane & 7;
     const float4* bufr = buf + rsub * EPI_PITCH4 + cg;          // + 4k * EPI_PITCH4 selects row 4k + rsub
     const bool per_batch_gate = (EPI == E2B_EPI_RESID) && d.gate && d.gate_bstride != 0;
@@ -246,7 +252,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       if constexpr (EPI == E2B_EPI_GEGLU) {
         static_assert(BN == 256 || EPI != E2B_EPI_GEGLU, "GEGLU packs 128 value + 128 gate columns per tile");
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
+        for (int c = cw; c < BN / 64; c += CSTEP) {
           uint32_t v[32];
           float4 gt[8];
           tmem_ld32(taddr + BN / 2 + c * 32, v);     // gate half first
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
         }
       } else if constexpr (EPI == E2B_EPI_QKV) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = cw; c < BN / 32; c += CSTEP) {
           const int col0 = n0 + c * 32;
           if (col0 >= d.N) break;
           const int col = col0 + cg * 4;
@@ -405,17 +411,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
           }
           __syncwarp();
         };
-        float4 preA[8], preB[8];
-        float4 biasA, gateA, biasB, gateB;
-        load_ops(0, preA, biasA, gateA);
+        if constexpr (EW == 4) {
+          // two operand sets, used alternately (no register copies that would wait on the in-flight loads)
+          float4 preA[8], preB[8];
+          float4 biasA, gateA, biasB, gateB;
+          load_ops(0, preA, biasA, gateA);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; c += 2) {
-          if (c * 32 >= ncols) break;
-          load_ops(c + 1, preB, biasB, gateB);
-          process(c, preA, biasA, gateA);
-          if ((c + 1) * 32 >= ncols) break;
-          load_ops(c + 2, preA, biasA, gateA);
-          process(c + 1, preB, biasB, gateB);
+          for (int c = 0; c < BN / 32; c += 2) {
+            if (c * 32 >= ncols) break;
+            load_ops(c + 1, preB, biasB, gateB);
+            process(c, preA, biasA, gateA);
+            if ((c + 1) * 32 >= ncols) break;
+            load_ops(c + 2, preA, biasA, gateA);
+            process(c + 1, preB, biasB, gateB);
+          }
+        } else {
+          // 8 epilogue warps: latency is covered by the second warp on each scheduler instead of a second operand set
+          float4 preA[8];
+          float4 biasA, gateA;
+#pragma unroll 1
+          for (int c = cw; c < BN / 32; c += CSTEP) {
+            if (c * 32 >= ncols) break;
+            load_ops(c, preA, biasA, gateA);
+            process(c, preA, biasA, gateA);
+          }
         }
       }
       tc_fence_before();
@@ -496,12 +515,12 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int EW>
 static int launch_t(const GemmArgs& a, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EW>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { e2b_set_kernel_error("gemm smem attribute: %s", cudaGetErrorString(e)); return -1; }
     configured = true;
   }
@@ -512,7 +531,7 @@ static int launch_t(const GemmArgs& a, cudaStream_t st) {
   const double out_bytes = (EPI == E2B_EPI_F32) ? 4.0 : (EPI == E2B_EPI_RESID ? 8.0 : 2.0);
   ProfScope ps(st, kinds[EPI], a.d.M, a.d.N, a.d.K, 2.0 * a.d.M * a.d.N * a.d.K,
                2.0 * ((double)a.d.M * a.d.K + (double)a.d.N * a.d.K) + out_bytes * a.d.M * out_cols + (a.d.out_b16 ? 2.0 * a.d.M * out_cols : 0.0));
-  gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a);
+  gemm_kernel<BN, EPI, EW><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { e2b_set_kernel_error("gemm launch: %s", cudaGetErrorString(e)); return -1; }
   return 0;
@@ -529,6 +548,9 @@ extern "C" void e2b_set_kernel_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* e2b_kernel_last_error(void) { return g_err; }
+
+// K threshold (inclusive) below which the 8-epilogue-warp configuration is used; settable for tuning / A-B tests.
+extern "C" int e2b_gemm_ew8_max_k = 1536;   // tools/bench_gemm3.py: 8 warps win up to K=1280, tie at 2048, lose at 5120
 
 extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
   if (d->M <= 0 || d->N <= 0) return 0;
@@ -559,19 +581,20 @@ extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
     return -1;
   }
   if (make_tmap_bf16(&a.tmB, d->w, d->N, d->K, d->ldw, bn256 ? 256 : 128)) return -1;
-#define E2B_DISPATCH(BN_)                                                             \
+#define E2B_DISPATCH(BN_, EW_)                                                        \
   switch (d->epi) {                                                                   \
-    case E2B_EPI_BF16: return launch_t<BN_, E2B_EPI_BF16>(a, stream);                 \
-    case E2B_EPI_F32: return launch_t<BN_, E2B_EPI_F32>(a, stream);                   \
-    case E2B_EPI_RESID: return launch_t<BN_, E2B_EPI_RESID>(a, stream);               \
-    case E2B_EPI_QKV: return launch_t<BN_, E2B_EPI_QKV>(a, stream);                   \
+    case E2B_EPI_BF16: return launch_t<BN_, E2B_EPI_BF16, EW_>(a, stream);            \
+    case E2B_EPI_F32: return launch_t<BN_, E2B_EPI_F32, EW_>(a, stream);              \
+    case E2B_EPI_RESID: return launch_t<BN_, E2B_EPI_RESID, EW_>(a, stream);          \
+    case E2B_EPI_QKV: return launch_t<BN_, E2B_EPI_QKV, EW_>(a, stream);              \
     default: break;                                                                   \
   }
+  const bool ew8 = d->K <= e2b_gemm_ew8_max_k;   // small K: epilogue-bound, use 8 epilogue warps + 3 stages
   if (bn256) {
-    if (d->epi == E2B_EPI_GEGLU) return launch_t<256, E2B_EPI_GEGLU>(a, stream);
-    E2B_DISPATCH(256)
+    if (d->epi == E2B_EPI_GEGLU) return ew8 ? launch_t<256, E2B_EPI_GEGLU, 8>(a, stream) : launch_t<256, E2B_EPI_GEGLU, 4>(a, stream);
+    if (ew8) { E2B_DISPATCH(256, 8) } else { E2B_DISPATCH(256, 4) }
   } else {
-    E2B_DISPATCH(128)
+    E2B_DISPATCH(128, 4)
   }
 #undef E2B_DISPATCH
   e2b_set_kernel_error("gemm: unknown epilogue %d", d->epi);
