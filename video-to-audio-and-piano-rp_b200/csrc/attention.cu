@@ -52,12 +52,21 @@ struct AttnArgs {
   CUtensorMap tmQ, tmK, tmV;
   e2b_attn_desc d;
   ClampPoly cp;
+  long long* dbg;
 };
 
 // Persistent kernel: one CTA per SM loops over work items (q-tile, head, sequence).  The TMA producer and the MMA issuer
 // run ahead across item boundaries (Q and O are double-buffered, K/V tiles stream through one ring for all items), so the
 // softmax warps never see a per-item prologue: ncu on the one-CTA-per-item version showed ~14 % of their samples waiting
 // for the first S tile of each CTA plus the launch/alloc/teardown of 14 336 CTAs per call.
+// Optional timeline for tools/attn_timeline.py: CTA 0 stamps clock64 per KV tile into dbg[g * 8 + slot] (null in production).
+static long long* g_att_dbg_host = nullptr;      // set by e2b_attention_set_debug; passed to the kernel as an argument
+constexpr int ATT_DBG_TILES = 96;
+#define dbg_stamp(g, slot)                                                                                      \
+  do {                                                                                                          \
+    if (args.dbg != nullptr && blockIdx.x == 0 && (g) < ATT_DBG_TILES) args.dbg[(g) * 8 + (slot)] = clock64();   \
+  } while (0)
+
 struct ItemCursor {          // iterates the (item, kv-tile) sequence of this CTA; every role walks the same sequence
   int it, item, j, nt, b, h, qt, kvb, kv_len;
   bool valid;
@@ -115,7 +124,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qtiles = (d.q_rows_per_batch + ATT_BQ - 1) / ATT_BQ;
   const int total = qtiles * d.heads * d.batch;
-  constexpr uint32_t NSOFT = 32 * ATT_SOFTMAX_WARPS;
+  // One elected arrival per softmax warp (after __syncwarp): mbarrier arrivals are lane-serialised shared-memory atomics, and
+  // 512 per-thread arrivals on two barriers per S tile sat on the critical path (ncu: warps spinning on s_full, no pipe busy).
+  constexpr uint32_t NSOFT = ATT_SOFTMAX_WARPS;
 
   if (warp == ATT_W_TMA && lane == 0) {
     tma_prefetch_desc(&args.tmQ);
@@ -150,8 +161,25 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
 
   if (warp == ATT_W_TMA && lane == 0) {
     // ------------------------------------------------------------ TMA producer
-    ItemCursor c;
+    // The K/V working set of a call (hundreds of MB) does not live in L2, and a tile can only be requested into shared
+    // memory once its ring slot is free, i.e. at most ATT_KV tiles ahead: measured ~3.9K cycles from issue to landing, which
+    // set the whole kernel's pace.  A second cursor therefore runs ATT_PF tiles further ahead and asks the TMA unit to pull
+    // those tiles into L2 (no shared-memory cost), so the real loads are L2 hits.
+    constexpr int ATT_PF = 6;
+    ItemCursor c, pf;
     cursor_init(c, d, qtiles, total);
+    cursor_init(pf, d, qtiles, total);
+    auto prefetch_tile = [&](const ItemCursor& t) {
+      if (t.j == 0) tma_prefetch_l2_2d(&args.tmQ, d.q_col0 + t.h * ATT_D, t.b * d.q_rows_per_batch + t.qt * ATT_BQ);
+      tma_prefetch_l2_2d(&args.tmK, d.k_col0 + t.h * ATT_D, t.kvb * d.kv_rows_per_batch + t.j * ATT_BK);
+      const int vr = (t.kvb * d.heads + t.h) * ATT_D;
+      tma_prefetch_l2_2d(&args.tmV, t.j * ATT_BK, vr);
+      tma_prefetch_l2_2d(&args.tmV, t.j * ATT_BK + 64, vr);
+    };
+    for (int i = 0; i < ATT_PF + ATT_KV && pf.valid; ++i) {
+      prefetch_tile(pf);
+      cursor_next_tile(pf, d, qtiles, total);
+    }
     int g = 0;
     while (c.valid) {
       const int qb = c.it & 1;
@@ -162,27 +190,33 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       for (int j = 0; j < c.nt; ++j, ++g) {
         const int s = g % ATT_KV;
         mbar_wait(&kv_empty[s], ((g / ATT_KV) & 1) ^ 1);
+        dbg_stamp(g, 0);
         mbar_arrive_expect_tx(&kv_full[s], 32768);
         tma_load_2d(smem + ATT_SK + s * 16384, &args.tmK, &kv_full[s], d.k_col0 + c.h * ATT_D, c.kvb * d.kv_rows_per_batch + j * ATT_BK);
         tma_load_2d(smem + ATT_SV + s * 16384, &args.tmV, &kv_full[s], j * ATT_BK, vrow);
         tma_load_2d(smem + ATT_SV + s * 16384 + 8192, &args.tmV, &kv_full[s], j * ATT_BK + 64, vrow);
+        if (pf.valid) {
+          prefetch_tile(pf);
+          cursor_next_tile(pf, d, qtiles, total);
+        }
       }
       cursor_next_item(c, d, qtiles, total);
     }
   } else if (warp == ATT_W_MMA && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer: S runs one tile ahead of PV, across items
+    // ------------------------------------------------------------ S = Q K^T issuer
+    // Two issuing threads (this one and the PV issuer below) in different warps / schedulers: a clock64 timeline showed a single
+    // thread needs ~1000 cycles to issue one PV group (8 tcgen05.mma + commits), ~350 for one S group and ~90 per mbarrier
+    // probe -- ~3K cycles of serial work per tile, which (not the softmax, ~1.9K) set the kernel's pace.
     constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, ATT_BK);
-    constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, ATT_D);
-    ItemCursor cs, cp;                 // S cursor (ahead) and PV cursor
+    ItemCursor cs;
     cursor_init(cs, d, qtiles, total);
-    cursor_init(cp, d, qtiles, total);
-    int gs = 0, gp = 0;
-    auto issue_s = [&]() {
+    for (int gs = 0; cs.valid; ++gs) {
       const int sb = gs & 1, ks = gs % ATT_KV, qb = cs.it & 1;
       if (cs.j == 0) mbar_wait(&q_full[qb], (cs.it >> 1) & 1);
       mbar_wait(&kv_full[ks], (gs / ATT_KV) & 1);
       mbar_wait(&s_empty[sb], ((gs >> 1) & 1) ^ 1);
       tc_fence_after();
+      dbg_stamp(gs, 1);
       const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SQ + qb * 16384));
       const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SK + ks * 16384));
 #pragma unroll
@@ -190,28 +224,34 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         umma_bf16_ss(tmem_base + sb * ATT_BK, dq + k * UMMA_K_STEP_ENC, dk + k * UMMA_K_STEP_ENC, idesc_s, k != 0 ? 1u : 0u);
       umma_commit(&s_full[sb]);
       if (cs.j == cs.nt - 1) umma_commit(&q_empty[qb]);          // Q buffer is free once the item's last S has completed
-      ++gs;
+      dbg_stamp(gs, 4);
       cursor_next_tile(cs, d, qtiles, total);
-    };
-    if (cs.valid) issue_s();
-    while (cp.valid) {
-      if (cs.valid) issue_s();
+    }
+  } else if (warp == ATT_W_ALLOC && lane == 0) {
+    // ------------------------------------------------------------ O += P V issuer
+    constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, ATT_D);
+    ItemCursor cp;
+    cursor_init(cp, d, qtiles, total);
+    for (int gp = 0; cp.valid; ++gp) {
       const int pb = gp & 1, ks = gp % ATT_KV, ob = cp.it & 1;
       mbar_wait(&p_full[pb], (gp >> 1) & 1);
       if (cp.j == 0) mbar_wait(&o_empty[ob], ((cp.it >> 1) & 1) ^ 1);
       tc_fence_after();
+      dbg_stamp(gp, 2);
       const uint32_t tmem_o = tmem_base + 256 + ob * ATT_D;
+      const uint64_t dp0 = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SP + pb * 32768));
+      const uint64_t dv0 = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SV + ks * 16384));
 #pragma unroll
       for (int kk = 0; kk < ATT_BK / 16; ++kk) {
-        const int atom = kk >> 2, k4 = kk & 3;
-        const uint64_t dp = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SP + pb * 32768 + atom * 16384)) + k4 * UMMA_K_STEP_ENC;
-        const uint64_t dv = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SV + ks * 16384 + atom * 8192)) + k4 * UMMA_K_STEP_ENC;
+        // atom (kk >> 2): +16 KB for P, +8 KB for V^T (encoded >> 4); then 32 B per 16-key step inside the swizzle atom
+        const uint64_t dp = dp0 + (uint64_t)((kk >> 2) * (16384 >> 4) + (kk & 3) * UMMA_K_STEP_ENC);
+        const uint64_t dv = dv0 + (uint64_t)((kk >> 2) * (8192 >> 4) + (kk & 3) * UMMA_K_STEP_ENC);
         umma_bf16_ss(tmem_o, dp, dv, idesc_o, (cp.j | kk) != 0 ? 1u : 0u);
       }
-      umma_commit(&kv_empty[ks]);
+      umma_commit(&kv_empty[ks]);      // S(g) finished long before P(g) existed, so this also covers K of the slot
       umma_commit(&p_empty[pb]);
       if (cp.j == cp.nt - 1) umma_commit(&o_full[ob]);
-      ++gp;
+      dbg_stamp(gp, 3);
       cursor_next_tile(cp, d, qtiles, total);
     }
   } else if (warp < ATT_SOFTMAX_WARPS) {
@@ -234,6 +274,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       const bool q_valid = q_pos < d.q_rows_per_batch;
       const bool warp_valid = (c.qt * ATT_BQ + quarter * 32) < d.q_rows_per_batch;
       float l0 = 0.f, l1 = 0.f;
+      // value-head gate of this row: loaded now, used after the last tile (an exposed global load in the item epilogue before)
+      const float gate_v = (d.hgate && q_valid) ? __ldg(d.hgate + (size_t)(c.b * d.q_rows_per_batch + q_pos) * d.hgate_ld + c.h) : 1.0f;
       for (int j = 0; j < c.nt; ++j, ++g) {
         const int s = g & 1;
         const uint32_t ph = (g >> 1) & 1;
@@ -293,10 +335,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           }
         }
-        tc_fence_before();
-        mbar_arrive(&s_empty[s]);
-        fence_proxy_async_smem();
-        mbar_arrive(&p_full[s]);
+        if (warp == 0 && lane == 0) dbg_stamp(g, 5);
+        tc_fence_before();             // this lane's tcgen05.ld of S are complete (tcgen05.wait::ld above)
+        fence_proxy_async_smem();      // this lane's P stores are visible to the async proxy (tensor core)
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&s_empty[s]);
+          mbar_arrive(&p_full[s]);
+        }
       }
 
       // item epilogue: combine the four column quarters' row sums, read O, scale, store
@@ -308,16 +354,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       mbar_wait(&o_full[ob], (c.it >> 1) & 1);
       tc_fence_after();
       float scale = 0.f;
-      if (q_valid && l > 0.f) {
-        scale = 1.0f / l;
-        if (d.hgate) scale *= __ldg(d.hgate + (size_t)(c.b * d.q_rows_per_batch + q_pos) * d.hgate_ld + c.h);
-      }
+      if (q_valid && l > 0.f) scale = gate_v / l;
       {
         uint32_t v[16];
         tmem_ld16(tmem_base + 256 + ob * ATT_D + lane_base + cq * 16, v);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&o_empty[ob]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[ob]);
         if (q_valid) {
           __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)(c.b * d.q_rows_per_batch + q_pos) * d.ldo + c.h * ATT_D + cq * 16;
           uint4* o4 = reinterpret_cast<uint4*>(op);
@@ -345,12 +389,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
 
 using namespace e2b;
 
+extern "C" int e2b_attention_set_debug(long long* dev_buf) {
+  e2b::g_att_dbg_host = dev_buf;
+  return 0;
+}
+
 extern "C" int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream) {
   if (d->batch <= 0 || d->heads <= 0 || d->q_rows_per_batch <= 0) return 0;
   if (d->kv_rows_per_batch <= 0) { e2b_set_kernel_error("attention: kv_rows_per_batch must be positive"); return -1; }
   if ((d->ldo % 8) || (reinterpret_cast<uintptr_t>(d->out) & 15)) { e2b_set_kernel_error("attention: out must be 16-byte aligned"); return -1; }
   AttnArgs a;
   a.d = *d;
+  a.dbg = g_att_dbg_host;
   {
     const double L2E = 1.4426950408889634, c = d->softclamp > 0 ? d->softclamp : 50.0, c2 = c * c;
     a.cp.c0 = (float)L2E;

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 32 * EW);
+      mbar_init(&tempty[s], EW);
     }
     fence_mbar_init();
   }
@@ -442,7 +442,8 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[as]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);     // one arrival per epilogue warp
     }
   }
 
