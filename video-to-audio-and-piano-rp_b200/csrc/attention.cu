@@ -159,7 +159,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == ATT_W_TMA && lane == 0) {
+  // Producer / issuer roles run on their whole warp with uniform control flow; only the TMA / MMA / commit instructions are
+  // under elect_one() (a `lane == 0` role branch makes the compiler wrap every UTCHMMA / UTMALDG in a divergence loop).
+  if (warp == ATT_W_TMA) {
     // ------------------------------------------------------------ TMA producer
     // The K/V working set of a call (hundreds of MB) does not live in L2, and a tile can only be requested into shared
     // memory once its ring slot is free, i.e. at most ATT_KV tiles ahead: measured ~3.9K cycles from issue to landing, which
@@ -177,32 +179,37 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       tma_prefetch_l2_2d(&args.tmV, t.j * ATT_BK + 64, vr);
     };
     for (int i = 0; i < ATT_PF + ATT_KV && pf.valid; ++i) {
-      prefetch_tile(pf);
+      if (elect_one()) prefetch_tile(pf);
+      __syncwarp();
       cursor_next_tile(pf, d, qtiles, total);
     }
     int g = 0;
     while (c.valid) {
       const int qb = c.it & 1;
       mbar_wait(&q_empty[qb], ((c.it >> 1) & 1) ^ 1);
-      mbar_arrive_expect_tx(&q_full[qb], 16384);
-      tma_load_2d(smem + ATT_SQ + qb * 16384, &args.tmQ, &q_full[qb], d.q_col0 + c.h * ATT_D, c.b * d.q_rows_per_batch + c.qt * ATT_BQ);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&q_full[qb], 16384);
+        tma_load_2d(smem + ATT_SQ + qb * 16384, &args.tmQ, &q_full[qb], d.q_col0 + c.h * ATT_D, c.b * d.q_rows_per_batch + c.qt * ATT_BQ);
+      }
+      __syncwarp();
       const int vrow = (c.kvb * d.heads + c.h) * ATT_D;
       for (int j = 0; j < c.nt; ++j, ++g) {
         const int s = g % ATT_KV;
         mbar_wait(&kv_empty[s], ((g / ATT_KV) & 1) ^ 1);
-        dbg_stamp(g, 0);
-        mbar_arrive_expect_tx(&kv_full[s], 32768);
-        tma_load_2d(smem + ATT_SK + s * 16384, &args.tmK, &kv_full[s], d.k_col0 + c.h * ATT_D, c.kvb * d.kv_rows_per_batch + j * ATT_BK);
-        tma_load_2d(smem + ATT_SV + s * 16384, &args.tmV, &kv_full[s], j * ATT_BK, vrow);
-        tma_load_2d(smem + ATT_SV + s * 16384 + 8192, &args.tmV, &kv_full[s], j * ATT_BK + 64, vrow);
-        if (pf.valid) {
-          prefetch_tile(pf);
-          cursor_next_tile(pf, d, qtiles, total);
+        if (elect_one()) {
+          dbg_stamp(g, 0);
+          mbar_arrive_expect_tx(&kv_full[s], 32768);
+          tma_load_2d(smem + ATT_SK + s * 16384, &args.tmK, &kv_full[s], d.k_col0 + c.h * ATT_D, c.kvb * d.kv_rows_per_batch + j * ATT_BK);
+          tma_load_2d(smem + ATT_SV + s * 16384, &args.tmV, &kv_full[s], j * ATT_BK, vrow);
+          tma_load_2d(smem + ATT_SV + s * 16384 + 8192, &args.tmV, &kv_full[s], j * ATT_BK + 64, vrow);
+          if (pf.valid) prefetch_tile(pf);
         }
+        __syncwarp();
+        if (pf.valid) cursor_next_tile(pf, d, qtiles, total);
       }
       cursor_next_item(c, d, qtiles, total);
     }
-  } else if (warp == ATT_W_MMA && lane == 0) {
+  } else if (warp == ATT_W_MMA) {
     // ------------------------------------------------------------ S = Q K^T issuer
     // Two issuing threads (this one and the PV issuer below) in different warps / schedulers: a clock64 timeline showed a single
     // thread needs ~1000 cycles to issue one PV group (8 tcgen05.mma + commits), ~350 for one S group and ~90 per mbarrier
@@ -216,18 +223,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       mbar_wait(&kv_full[ks], (gs / ATT_KV) & 1);
       mbar_wait(&s_empty[sb], ((gs >> 1) & 1) ^ 1);
       tc_fence_after();
-      dbg_stamp(gs, 1);
-      const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SQ + qb * 16384));
-      const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SK + ks * 16384));
+      if (elect_one()) {
+        dbg_stamp(gs, 1);
+        const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SQ + qb * 16384));
+        const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SK + ks * 16384));
 #pragma unroll
-      for (int k = 0; k < ATT_D / 16; ++k)
-        umma_bf16_ss(tmem_base + sb * ATT_BK, dq + k * UMMA_K_STEP_ENC, dk + k * UMMA_K_STEP_ENC, idesc_s, k != 0 ? 1u : 0u);
-      umma_commit(&s_full[sb]);
-      if (cs.j == cs.nt - 1) umma_commit(&q_empty[qb]);          // Q buffer is free once the item's last S has completed
-      dbg_stamp(gs, 4);
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_bf16_ss(tmem_base + sb * ATT_BK, dq + k * UMMA_K_STEP_ENC, dk + k * UMMA_K_STEP_ENC, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[sb]);
+        if (cs.j == cs.nt - 1) umma_commit(&q_empty[qb]);          // Q buffer is free once the item's last S has completed
+        dbg_stamp(gs, 4);
+      }
+      __syncwarp();
       cursor_next_tile(cs, d, qtiles, total);
     }
-  } else if (warp == ATT_W_ALLOC && lane == 0) {
+  } else if (warp == ATT_W_ALLOC) {
     // ------------------------------------------------------------ O += P V issuer
     constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, ATT_D);
     ItemCursor cp;
@@ -237,6 +247,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       mbar_wait(&p_full[pb], (gp >> 1) & 1);
       if (cp.j == 0) mbar_wait(&o_empty[ob], ((cp.it >> 1) & 1) ^ 1);
       tc_fence_after();
+      if (elect_one()) {
       dbg_stamp(gp, 2);
       const uint32_t tmem_o = tmem_base + 256 + ob * ATT_D;
       const uint64_t dp0 = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SP + pb * 32768));
@@ -252,6 +263,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       umma_commit(&p_empty[pb]);
       if (cp.j == cp.nt - 1) umma_commit(&o_full[ob]);
       dbg_stamp(gp, 3);
+      }
+      __syncwarp();
       cursor_next_tile(cp, d, qtiles, total);
     }
   } else if (warp < ATT_SOFTMAX_WARPS) {

@@ -158,7 +158,10 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == W_TMA && lane == 0) {
+  // The producer and MMA roles are executed by their WHOLE warp with warp-uniform control flow; only the TMA / MMA / commit
+  // instructions sit under elect_one().  (With `lane == 0` role branches every UTCHMMA / UTMALDG was wrapped by the compiler in
+  // a divergence loop -- R2UR moves, ELECT, predicate shuffles and a backward BRA.U.ANY -- costing ~100 cycles per MMA issue.)
+  if (warp == W_TMA) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
@@ -168,13 +171,16 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
       for (int kb = 0; kb < KB; ++kb) {
         while (kb >= args.kb_end[src]) { kb0 = args.kb_end[src]; ++src; }
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-        tma_load_2d(sA + stage * Cfg::A_BYTES, &args.tmA[src], &full[stage], (kb - kb0) * BK, m0);
-        tma_load_2d(sB + stage * Cfg::B_BYTES, &args.tmB, &full[stage], kb * BK, n0);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sA + stage * Cfg::A_BYTES, &args.tmA[src], &full[stage], (kb - kb0) * BK, m0);
+          tma_load_2d(sB + stage * Cfg::B_BYTES, &args.tmB, &full[stage], kb * BK, n0);
+        }
+        __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == W_MMA && lane == 0) {
+  } else if (warp == W_MMA) {
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
     int stage = 0;
@@ -189,13 +195,16 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
-        const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
+        if (elect_one()) {
+          const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
+          const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          umma_bf16_ss(tmem_d, da + k * UMMA_K_STEP_ENC, db + k * UMMA_K_STEP_ENC, idesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(&empty[stage]);
-        if (kb == KB - 1) umma_commit(&tfull[as]);
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_ss(tmem_d, da + k * UMMA_K_STEP_ENC, db + k * UMMA_K_STEP_ENC, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (kb == KB - 1) umma_commit(&tfull[as]);
+        }
+        __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
