@@ -5,7 +5,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, 'video-to-audio-and-piano-rp_b200'), os
 import torch
 from e2_tts_pytorch import _lib
 from gpu_util import attention, DEV
-B, H, N = 16, 16, 782
+B, H, N = int(os.environ.get('BATCH', 16)), 16, 782
 HD = H * 64
 qk = (torch.randn(B * N, 2 * HD, device=DEV) * 0.5).to(torch.bfloat16)
 VLD = int(os.environ.get('VLD', 784))
@@ -26,9 +26,14 @@ e0.record(); attention(**kw); e1.record(); torch.cuda.synchronize()
 print(f'kernel {e0.elapsed_time(e1)*1e3:.1f} us for {B*H*7} items on 148 CTAs')
 L.e2b_attention_set_debug(C.c_void_p(0))
 t = dbg.cpu()[:96 * 8].reshape(96, 8)
-t0 = int(t[0, 0])
-names = ['tma_issue', 'S_pre', 'PV_pre', 'PV_post', 'S_post', 'sm_done_w0', '-', '-']
-print('tile ' + ' '.join(f'{n:>10s}' for n in names))
+t0 = int(t[0, 5])
+names = ['sm_done', 'S_pre', 'PV_pre', 'PV_post', 'S_post', 'sm_arrive', 's_full_ok', 'p_empty_ok']
+print('tile ' + ' '.join(f'{n:>10s}' for n in names) + ' | waitS waitP compute gap period')
+prev = None
 for g in range(int(os.environ.get('ROWS', 12))):
     row = [int(v) - t0 if int(v) else -1 for v in t[g]]
-    print(f'{g:4d} ' + ' '.join(f'{v:10d}' for v in row))
+    done, arr, sok, pok = row[0], row[5], row[6], row[7]
+    per = done - prev if prev is not None else 0
+    gap = arr - prev if prev is not None else 0
+    prev = done
+    print(f'{g:4d} ' + ' '.join(f'{v:10d}' for v in row) + f' | {sok-arr:5d} {pok-sok:5d} {done-pok:7d} {gap:4d} {per:6d}')

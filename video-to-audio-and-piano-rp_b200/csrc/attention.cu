@@ -27,20 +27,23 @@ constexpr int ATT_THREADS = 128 + 32 * ATT_SOFTMAX_WARPS;
 constexpr int ATT_W_TMA = ATT_SOFTMAX_WARPS, ATT_W_MMA = ATT_SOFTMAX_WARPS + 1, ATT_W_ALLOC = ATT_SOFTMAX_WARPS + 2;
 constexpr int ATT_BQ = 128, ATT_BK = 128, ATT_D = 64;
 constexpr int ATT_KV = 3;                       // K/V ring depth
+constexpr int ATT_ON = 80;                      // PV MMA N: 64 value channels + a ones row (col 64 = row sum of P) + 15 zero rows
+constexpr int ATT_VATOM = ATT_ON * 128;         // one V^T swizzle atom: 80 rows x 128 B (rows 64..79 are constants written once)
+constexpr int ATT_VSTAGE = 2 * ATT_VATOM;       // two 64-key atoms per 128-key tile
 constexpr int ATT_SQ = 0;                       // 2 x 16 KB  Q   [128 q, 64 d]        (double-buffered across work items)
 constexpr int ATT_SK = 2 * 16384;               // ATT_KV x 16 KB  K   [128 keys, 64 d]
-constexpr int ATT_SV = ATT_SK + ATT_KV * 16384; // ATT_KV x 16 KB  V^T 2 x [64 d, 64 keys]
-constexpr int ATT_SP = ATT_SV + ATT_KV * 16384; // 2 x 32 KB  P   2 x [128 q, 64 keys]
-constexpr int ATT_LSUM = ATT_SP + 2 * 32768;    // 2 x (4 x 128 floats): per-row partial sums of the four column quarters
-constexpr int ATT_BAR = ATT_LSUM + 2 * 2048;
+constexpr int ATT_SV = ATT_SK + ATT_KV * 16384; // ATT_KV x 20 KB  V^T 2 x [80 rows, 64 keys]
+constexpr int ATT_SP = ATT_SV + ATT_KV * ATT_VSTAGE; // 2 x 32 KB  P   2 x [128 q, 64 keys]
+constexpr int ATT_BAR = ATT_SP + 2 * 32768;
 constexpr int ATT_SMEM = ATT_BAR + 256;
-constexpr uint32_t ATT_TMEM_COLS = 512;         // S0 @0, S1 @128, O0 @256, O1 @320
+constexpr uint32_t ATT_TMEM_COLS = 512;         // S0 @0, S1 @128, O0 @256, O1 @336 (80 columns each)
+constexpr uint32_t ATT_TMEM_O = 256;
 
 // Soft-clamp + exponent in one polynomial.  With w = z^2 and |z| / clamp < 0.5,
 //   log2(e) * clamp * tanh(z / clamp) = z * (c0 + w (c1 + w (c2 + w (c3 + w c4))))     (abs. error < 3e-4 in the exponent
 // at the edge, < 1e-5 for |z/clamp| < 0.3), i.e. 6 FMA-pipe ops and ONE MUFU (ex2) per logit instead of tanh.approx (only
 // 2^-11 accurate, amplified 50x by the exp) + ex2.  Larger logits (rare) take the exact exp-based tanh.
-struct ClampPoly { float c0, c1, c2, c3, c4, wmax, clamp; };
+struct ClampPoly { float c0, c1, c2, c3, c4, wmax, clamp, wlo; };
 
 __device__ __forceinline__ float softclamp_exp2_arg_exact(float z, float clamp) {
   const float x = z / clamp;
@@ -85,18 +88,30 @@ __device__ __forceinline__ void cursor_load(ItemCursor& c, const e2b_attn_desc& 
   c.nt = max(1, (c.kv_len + ATT_BK - 1) / ATT_BK);        // at least one (fully masked) tile so O is defined
   c.j = 0;
 }
-__device__ __forceinline__ void cursor_init(ItemCursor& c, const e2b_attn_desc& d, int qtiles, int total) {
-  c.it = 0;
-  c.item = blockIdx.x;
-  cursor_load(c, d, qtiles, total);
+// Every role walks the same item sequence.  `nx` is the successor item, loaded one item early so that the kv_lens
+// global load (and the index arithmetic) is never on the critical path of an item switch.
+struct ItemWalk {
+  ItemCursor c, nx;
+};
+__device__ __forceinline__ void walk_init(ItemWalk& w, const e2b_attn_desc& d, int qtiles, int total) {
+  w.c.it = 0;
+  w.c.item = blockIdx.x;
+  cursor_load(w.c, d, qtiles, total);
+  w.nx = w.c;
+  ++w.nx.it;
+  w.nx.item += gridDim.x;
+  cursor_load(w.nx, d, qtiles, total);
 }
-__device__ __forceinline__ void cursor_next_item(ItemCursor& c, const e2b_attn_desc& d, int qtiles, int total) {
-  ++c.it;
-  c.item += gridDim.x;
-  cursor_load(c, d, qtiles, total);
+__device__ __forceinline__ void walk_next_item(ItemWalk& w, const e2b_attn_desc& d, int qtiles, int total) {
+  w.c = w.nx;
+  if (w.c.valid) {
+    ++w.nx.it;
+    w.nx.item += gridDim.x;
+    cursor_load(w.nx, d, qtiles, total);
+  }
 }
-__device__ __forceinline__ void cursor_next_tile(ItemCursor& c, const e2b_attn_desc& d, int qtiles, int total) {
-  if (++c.j == c.nt) cursor_next_item(c, d, qtiles, total);
+__device__ __forceinline__ void walk_next_tile(ItemWalk& w, const e2b_attn_desc& d, int qtiles, int total) {
+  if (++w.c.j == w.c.nt) walk_next_item(w, d, qtiles, total);
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_constant__ AttnArgs args) {
@@ -154,6 +169,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     tmem_alloc(tmem_slot, ATT_TMEM_COLS);
     tmem_relinquish();
   }
+  // rows 64..79 of every V^T atom: row 64 = 1.0 (so column 64 of O accumulates the row sums of the bf16 P the MMA actually
+  // used), rows 65..79 = 0.  A whole 128-byte row is constant, so the 128-byte swizzle does not matter.  TMA only ever
+  // rewrites rows 0..63.
+  for (int i = threadIdx.x; i < ATT_KV * 2 * 16 * 8; i += ATT_THREADS) {
+    const int atom = i / 128, rem = i % 128, row = rem / 8, chunk = rem % 8;
+    const uint32_t one2 = 0x3F803F80u;   // two bf16 1.0
+    const uint32_t val = row == 0 ? one2 : 0u;
+    *reinterpret_cast<uint4*>(smem + ATT_SV + atom * ATT_VATOM + (64 + row) * 128 + chunk * 16) = make_uint4(val, val, val, val);
+  }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -168,9 +193,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     // set the whole kernel's pace.  A second cursor therefore runs ATT_PF tiles further ahead and asks the TMA unit to pull
     // those tiles into L2 (no shared-memory cost), so the real loads are L2 hits.
     constexpr int ATT_PF = 6;
-    ItemCursor c, pf;
-    cursor_init(c, d, qtiles, total);
-    cursor_init(pf, d, qtiles, total);
+    ItemWalk wc, wpf;
+    walk_init(wc, d, qtiles, total);
+    walk_init(wpf, d, qtiles, total);
+    ItemCursor& c = wc.c;
+    ItemCursor& pf = wpf.c;
     auto prefetch_tile = [&](const ItemCursor& t) {
       if (t.j == 0) tma_prefetch_l2_2d(&args.tmQ, d.q_col0 + t.h * ATT_D, t.b * d.q_rows_per_batch + t.qt * ATT_BQ);
       tma_prefetch_l2_2d(&args.tmK, d.k_col0 + t.h * ATT_D, t.kvb * d.kv_rows_per_batch + t.j * ATT_BK);
@@ -181,7 +208,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     for (int i = 0; i < ATT_PF + ATT_KV && pf.valid; ++i) {
       if (elect_one()) prefetch_tile(pf);
       __syncwarp();
-      cursor_next_tile(pf, d, qtiles, total);
+      walk_next_tile(wpf, d, qtiles, total);
     }
     int g = 0;
     while (c.valid) {
@@ -197,17 +224,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         const int s = g % ATT_KV;
         mbar_wait(&kv_empty[s], ((g / ATT_KV) & 1) ^ 1);
         if (elect_one()) {
-          dbg_stamp(g, 0);
           mbar_arrive_expect_tx(&kv_full[s], 32768);
           tma_load_2d(smem + ATT_SK + s * 16384, &args.tmK, &kv_full[s], d.k_col0 + c.h * ATT_D, c.kvb * d.kv_rows_per_batch + j * ATT_BK);
-          tma_load_2d(smem + ATT_SV + s * 16384, &args.tmV, &kv_full[s], j * ATT_BK, vrow);
-          tma_load_2d(smem + ATT_SV + s * 16384 + 8192, &args.tmV, &kv_full[s], j * ATT_BK + 64, vrow);
+          tma_load_2d(smem + ATT_SV + s * ATT_VSTAGE, &args.tmV, &kv_full[s], j * ATT_BK, vrow);
+          tma_load_2d(smem + ATT_SV + s * ATT_VSTAGE + ATT_VATOM, &args.tmV, &kv_full[s], j * ATT_BK + 64, vrow);
           if (pf.valid) prefetch_tile(pf);
         }
         __syncwarp();
-        if (pf.valid) cursor_next_tile(pf, d, qtiles, total);
+        if (pf.valid) walk_next_tile(wpf, d, qtiles, total);
       }
-      cursor_next_item(c, d, qtiles, total);
+      walk_next_item(wc, d, qtiles, total);
     }
   } else if (warp == ATT_W_MMA) {
     // ------------------------------------------------------------ S = Q K^T issuer
@@ -215,13 +241,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     // thread needs ~1000 cycles to issue one PV group (8 tcgen05.mma + commits), ~350 for one S group and ~90 per mbarrier
     // probe -- ~3K cycles of serial work per tile, which (not the softmax, ~1.9K) set the kernel's pace.
     constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, ATT_BK);
-    ItemCursor cs;
-    cursor_init(cs, d, qtiles, total);
+    ItemWalk ws;
+    walk_init(ws, d, qtiles, total);
+    ItemCursor& cs = ws.c;
     for (int gs = 0; cs.valid; ++gs) {
       const int sb = gs & 1, ks = gs % ATT_KV, qb = cs.it & 1;
       if (cs.j == 0) mbar_wait(&q_full[qb], (cs.it >> 1) & 1);
       mbar_wait(&kv_full[ks], (gs / ATT_KV) & 1);
       mbar_wait(&s_empty[sb], ((gs >> 1) & 1) ^ 1);
+      // S(g) and P(g) share the buffer index: waiting here for PV(g-2) to have consumed P(g-2) lets the softmax warps write
+      // P(g) as soon as they see s_full(g), without a second mbarrier probe (~240 cycles each even when already complete)
+      mbar_wait(&p_empty[sb], ((gs >> 1) & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
         dbg_stamp(gs, 1);
@@ -235,13 +265,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         dbg_stamp(gs, 4);
       }
       __syncwarp();
-      cursor_next_tile(cs, d, qtiles, total);
+      walk_next_tile(ws, d, qtiles, total);
     }
   } else if (warp == ATT_W_ALLOC) {
     // ------------------------------------------------------------ O += P V issuer
-    constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, ATT_D);
-    ItemCursor cp;
-    cursor_init(cp, d, qtiles, total);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, ATT_ON);
+    ItemWalk wp;
+    walk_init(wp, d, qtiles, total);
+    ItemCursor& cp = wp.c;
     for (int gp = 0; cp.valid; ++gp) {
       const int pb = gp & 1, ks = gp % ATT_KV, ob = cp.it & 1;
       mbar_wait(&p_full[pb], (gp >> 1) & 1);
@@ -249,14 +280,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       tc_fence_after();
       if (elect_one()) {
       dbg_stamp(gp, 2);
-      const uint32_t tmem_o = tmem_base + 256 + ob * ATT_D;
+      const uint32_t tmem_o = tmem_base + ATT_TMEM_O + ob * ATT_ON;
       const uint64_t dp0 = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SP + pb * 32768));
-      const uint64_t dv0 = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SV + ks * 16384));
+      const uint64_t dv0 = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SV + ks * ATT_VSTAGE));
 #pragma unroll
       for (int kk = 0; kk < ATT_BK / 16; ++kk) {
-        // atom (kk >> 2): +16 KB for P, +8 KB for V^T (encoded >> 4); then 32 B per 16-key step inside the swizzle atom
+        // atom (kk >> 2): +16 KB for P, +10 KB for V^T (encoded >> 4); then 32 B per 16-key step inside the swizzle atom
         const uint64_t dp = dp0 + (uint64_t)((kk >> 2) * (16384 >> 4) + (kk & 3) * UMMA_K_STEP_ENC);
-        const uint64_t dv = dv0 + (uint64_t)((kk >> 2) * (8192 >> 4) + (kk & 3) * UMMA_K_STEP_ENC);
+        const uint64_t dv = dv0 + (uint64_t)((kk >> 2) * (ATT_VATOM >> 4) + (kk & 3) * UMMA_K_STEP_ENC);
         umma_bf16_ss(tmem_o, dp, dv, idesc_o, (cp.j | kk) != 0 ? 1u : 0u);
       }
       umma_commit(&kv_empty[ks]);      // S(g) finished long before P(g) existed, so this also covers K of the slot
@@ -265,7 +296,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       dbg_stamp(gp, 3);
       }
       __syncwarp();
-      cursor_next_tile(cp, d, qtiles, total);
+      walk_next_tile(wp, d, qtiles, total);
     }
   } else if (warp < ATT_SOFTMAX_WARPS) {
     // ------------------------------------------------------------ softmax + epilogue
@@ -279,23 +310,59 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     const int c0 = cq * 32;                             // first key column of this warp inside the tile
     // P: keys c0..c0+31 live in swizzle atom (cq >> 1), 16-byte chunks ((cq & 1) * 4 + q) ^ (r & 7) of the 128-byte row
     const uint32_t p_off = (cq >> 1) * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
-    ItemCursor c;
-    cursor_init(c, d, qtiles, total);
+    ItemWalk wk;
+    walk_init(wk, d, qtiles, total);
+    ItemCursor& c = wk.c;
+    // Deferred item epilogue: O of item i is read out after the FIRST tile of item i+1, when its last PV has long completed,
+    // so the o_full wait and the stores are off the critical path (O and Q are double-buffered across items).
+    struct Pending {
+      bool valid, q_valid;
+      int ob;
+      uint32_t parity;
+      float gate;
+      __nv_bfloat16* out;
+    } pend;
+    pend.valid = false;
+    auto flush = [&](const Pending& pd) {
+      mbar_wait(&o_full[pd.ob], pd.parity);
+      tc_fence_after();
+      uint32_t v[16], ls[1];
+      tmem_ld16(tmem_base + ATT_TMEM_O + pd.ob * ATT_ON + lane_base + cq * 16, v);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(ls[0]) : "r"(tmem_base + ATT_TMEM_O + pd.ob * ATT_ON + lane_base + 64) : "memory");
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[pd.ob]);
+      const float l = __uint_as_float(ls[0]);              // row sum of the bf16 probabilities, from the ones row of V^T
+      if (pd.q_valid) {
+        const float scale = l > 0.f ? pd.gate / l : 0.f;
+        uint4* o4 = reinterpret_cast<uint4*>(pd.out);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(v[8 * i + 0]) * scale, __uint_as_float(v[8 * i + 1]) * scale);
+          u.y = pack_bf16(__uint_as_float(v[8 * i + 2]) * scale, __uint_as_float(v[8 * i + 3]) * scale);
+          u.z = pack_bf16(__uint_as_float(v[8 * i + 4]) * scale, __uint_as_float(v[8 * i + 5]) * scale);
+          u.w = pack_bf16(__uint_as_float(v[8 * i + 6]) * scale, __uint_as_float(v[8 * i + 7]) * scale);
+          o4[i] = u;
+        }
+      }
+    };
     int g = 0;
     while (c.valid) {
       const int q_pos = c.qt * ATT_BQ + r;
       const bool q_valid = q_pos < d.q_rows_per_batch;
       const bool warp_valid = (c.qt * ATT_BQ + quarter * 32) < d.q_rows_per_batch;
-      float l0 = 0.f, l1 = 0.f;
-      // value-head gate of this row: loaded now, used after the last tile (an exposed global load in the item epilogue before)
+      // value-head gate of this row: loaded now, used in the (deferred) epilogue
       const float gate_v = (d.hgate && q_valid) ? __ldg(d.hgate + (size_t)(c.b * d.q_rows_per_batch + q_pos) * d.hgate_ld + c.h) : 1.0f;
       for (int j = 0; j < c.nt; ++j, ++g) {
         const int s = g & 1;
         const uint32_t ph = (g >> 1) & 1;
         const int nvalid = min(ATT_BK, c.kv_len - j * ATT_BK);
-        mbar_wait(&s_full[s], ph);
+        if (warp == 0 && lane == 0) dbg_stamp(g, 5);
+        mbar_wait(&s_full[s], ph);          // also guarantees that P buffer s is free (the S issuer waited for p_empty)
         tc_fence_after();
-        mbar_wait(&p_empty[s], ph ^ 1);
+        if (warp == 0 && lane == 0) dbg_stamp(g, 6);
         uint8_t* prow = smem + ATT_SP + s * 32768 + p_off;
         const bool live = warp_valid && c0 < nvalid;
 #pragma unroll
@@ -308,21 +375,35 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             float arg[16];
             float wm = 0.f;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float z = __uint_as_float(v[i]);
-              const float w = z * z;
-              wm = fmaxf(wm, w);
-              float q = fmaf(w, cp.c4, cp.c3);
-              q = fmaf(w, q, cp.c2);
-              q = fmaf(w, q, cp.c1);
-              q = fmaf(w, q, cp.c0);
-              arg[i] = z * q;
-            }
-            if (__any_sync(0xffffffffu, wm >= cp.wmax)) {
+            for (int i = 0; i < 16; ++i) wm = fmaxf(wm, fabsf(__uint_as_float(v[i])));
+            // The softmax warps are instruction-issue bound (timeline: IPC ~0.9 while computing), so the common case gets the
+            // shortest polynomial: for |z| <= wlo (|z/clamp| <= 0.16) the degree-5 series is exact to 1e-5 in the exponent.
+            if (!__any_sync(0xffffffffu, wm > cp.wlo)) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const float z = __uint_as_float(v[i]);
-                if (z * z >= cp.wmax) arg[i] = softclamp_exp2_arg_exact(z, cp.clamp);
+                const float w = z * z;
+                float q = fmaf(w, cp.c2, cp.c1);
+                q = fmaf(w, q, cp.c0);
+                arg[i] = z * q;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float z = __uint_as_float(v[i]);
+                const float w = z * z;
+                float q = fmaf(w, cp.c4, cp.c3);
+                q = fmaf(w, q, cp.c2);
+                q = fmaf(w, q, cp.c1);
+                q = fmaf(w, q, cp.c0);
+                arg[i] = z * q;
+              }
+              if (__any_sync(0xffffffffu, wm * wm >= cp.wmax)) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float z = __uint_as_float(v[i]);
+                  if (z * z >= cp.wmax) arg[i] = softclamp_exp2_arg_exact(z, cp.clamp);
+                }
               }
             }
             float p[16];
@@ -333,11 +414,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
               for (int i = 0; i < 16; ++i) p[i] = (c0 + hh * 16 + i < nvalid) ? p[i] : 0.f;
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              l0 += p[2 * i];
-              l1 += p[2 * i + 1];
-              pk[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
-            }
+            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) pk[i] = 0u;
@@ -348,7 +425,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           }
         }
-        if (warp == 0 && lane == 0) dbg_stamp(g, 5);
+        if (warp == 0 && lane == 0) dbg_stamp(g, 0);
         tc_fence_before();             // this lane's tcgen05.ld of S are complete (tcgen05.wait::ld above)
         fence_proxy_async_smem();      // this lane's P stores are visible to the async proxy (tensor core)
         __syncwarp();
@@ -356,41 +433,20 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
           mbar_arrive(&s_empty[s]);
           mbar_arrive(&p_full[s]);
         }
-      }
-
-      // item epilogue: combine the four column quarters' row sums, read O, scale, store
-      const int ob = c.it & 1;
-      float* lsum = reinterpret_cast<float*>(smem + ATT_LSUM + ob * 2048);
-      lsum[cq * 128 + r] = l0 + l1;
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * ATT_SOFTMAX_WARPS) : "memory");
-      const float l = (lsum[r] + lsum[128 + r]) + (lsum[256 + r] + lsum[384 + r]);
-      mbar_wait(&o_full[ob], (c.it >> 1) & 1);
-      tc_fence_after();
-      float scale = 0.f;
-      if (q_valid && l > 0.f) scale = gate_v / l;
-      {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + 256 + ob * ATT_D + lane_base + cq * 16, v);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_empty[ob]);
-        if (q_valid) {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)(c.b * d.q_rows_per_batch + q_pos) * d.ldo + c.h * ATT_D + cq * 16;
-          uint4* o4 = reinterpret_cast<uint4*>(op);
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            uint4 u;
-            u.x = pack_bf16(__uint_as_float(v[8 * i + 0]) * scale, __uint_as_float(v[8 * i + 1]) * scale);
-            u.y = pack_bf16(__uint_as_float(v[8 * i + 2]) * scale, __uint_as_float(v[8 * i + 3]) * scale);
-            u.z = pack_bf16(__uint_as_float(v[8 * i + 4]) * scale, __uint_as_float(v[8 * i + 5]) * scale);
-            u.w = pack_bf16(__uint_as_float(v[8 * i + 6]) * scale, __uint_as_float(v[8 * i + 7]) * scale);
-            o4[i] = u;
-          }
+        if (j == 0 && pend.valid) {    // previous item's O: its last PV completed during this tile
+          flush(pend);
+          pend.valid = false;
         }
       }
-      cursor_next_item(c, d, qtiles, total);
+      pend.valid = true;
+      pend.q_valid = q_valid;
+      pend.ob = c.it & 1;
+      pend.parity = (c.it >> 1) & 1;
+      pend.gate = gate_v;
+      pend.out = reinterpret_cast<__nv_bfloat16*>(d.out) + (size_t)(c.b * d.q_rows_per_batch + q_pos) * d.ldo + c.h * ATT_D + cq * 16;
+      walk_next_item(wk, d, qtiles, total);
     }
+    if (pend.valid) flush(pend);
   }
 
   tc_fence_before();
@@ -423,6 +479,7 @@ extern "C" int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream)
     a.cp.c4 = (float)(62.0 * L2E / (2835.0 * c2 * c2 * c2 * c2));
     a.cp.wmax = (float)(0.25 * c2);
     a.cp.clamp = (float)c;
+    a.cp.wlo = (float)(0.16 * c);
   }
   const uint64_t q_rows = (uint64_t)d->batch * d->q_rows_per_batch;
   const int kv_batches = d->kv_batch_mod > 0 ? d->kv_batch_mod : d->batch;
