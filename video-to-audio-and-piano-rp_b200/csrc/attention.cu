@@ -43,12 +43,37 @@ constexpr uint32_t ATT_TMEM_O = 256;
 //   log2(e) * clamp * tanh(z / clamp) = z * (c0 + w (c1 + w (c2 + w (c3 + w c4))))     (abs. error < 3e-4 in the exponent
 // at the edge, < 1e-5 for |z/clamp| < 0.3), i.e. 6 FMA-pipe ops and ONE MUFU (ex2) per logit instead of tanh.approx (only
 // 2^-11 accurate, amplified 50x by the exp) + ex2.  Larger logits (rare) take the exact exp-based tanh.
-struct ClampPoly { float c0, c1, c2, c3, c4, wmax, clamp, wlo; };
+struct ClampPoly { float c0, c1, c2, c3, c4, wmax, clamp, wlo, ex_a, ex_b; };
 
-__device__ __forceinline__ float softclamp_exp2_arg_exact(float z, float clamp) {
-  const float x = z / clamp;
-  const float e = ex2_approx(x * 2.8853900817779268f);     // exp(2x)
-  return (1.0f - __fdividef(2.0f, 1.0f + e)) * clamp * 1.4426950408889634f;
+// log2(e) * clamp * tanh(z / clamp) from the exp-based identity; ex_a = 2 log2(e) / clamp, ex_b = log2(e) * clamp
+__device__ __forceinline__ float softclamp_exp2_arg_exact(float z, float ex_a, float ex_b) {
+  const float e = ex2_approx(z * ex_a);                    // exp(2 z / clamp)
+  return fmaf(-2.0f * ex_b, __frcp_rn(1.0f + e), ex_b);
+}
+
+// p = 2^(z * poly(z^2)) for the 32 logits of one warp-tile, packed to bf16 pairs, in packed-pair arithmetic (FFMA2 / FMUL2:
+// half the issue slots of the scalar forms).  HI selects the degree-9 series.
+template <bool HI>
+__device__ __forceinline__ void exp_block(const uint32_t (&v)[32], const ClampPoly& cp, uint32_t (&pk)[16]) {
+  const uint64_t c0 = f32x2_pack(cp.c0, cp.c0), c1 = f32x2_pack(cp.c1, cp.c1), c2 = f32x2_pack(cp.c2, cp.c2);
+  const uint64_t c3 = f32x2_pack(cp.c3, cp.c3), c4 = f32x2_pack(cp.c4, cp.c4);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint64_t z = f32x2_pack(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+    const uint64_t w = f32x2_mul(z, z);
+    uint64_t q;
+    if (HI) {
+      q = f32x2_fma(w, c4, c3);
+      q = f32x2_fma(w, q, c2);
+      q = f32x2_fma(w, q, c1);
+    } else {
+      q = f32x2_fma(w, c2, c1);
+    }
+    q = f32x2_fma(w, q, c0);
+    float a0, a1;
+    f32x2_unpack(f32x2_mul(z, q), a0, a1);
+    pk[i] = pack_bf16(ex2_approx(a0), ex2_approx(a1));
+  }
 }
 
 struct AttnArgs {
@@ -365,65 +390,43 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         if (warp == 0 && lane == 0) dbg_stamp(g, 6);
         uint8_t* prow = smem + ATT_SP + s * 32768 + p_off;
         const bool live = warp_valid && c0 < nvalid;
+        uint32_t pk[16];
+        if (live) {
+          // One 32-column block per warp and tile: the polynomial (FMA pipe) and ex2 (MUFU pipe, 16/clk/SM: the binding unit of
+          // this kernel, tools/pipe_bench.cu) streams of the 32 logits sit in ONE basic block per tier so that they interleave;
+          // as two 16-column halves separated by the tier branch the four warps of a scheduler ran their FMA and MUFU phases in
+          // lockstep, back to back (timeline: 1850 clk per tile for 1024 clk of MUFU work).
+          uint32_t v[32];
+          tmem_ld32(tmem_base + lane_base + s * ATT_BK + c0, v);
+          tmem_ld_wait();
+          float wm = 0.f;
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {                  // two 16-column halves keep the register footprint small
-          uint32_t pk[8];
-          if (live) {
-            uint32_t v[16];
-            tmem_ld16(tmem_base + lane_base + s * ATT_BK + c0 + hh * 16, v);
-            tmem_ld_wait();
-            float arg[16];
-            float wm = 0.f;
+          for (int i = 0; i < 32; ++i) wm = fmaxf(wm, fabsf(__uint_as_float(v[i])));
+          if (!__any_sync(0xffffffffu, wm > cp.wlo)) {
+            exp_block<false>(v, cp, pk);                  // |z/clamp| <= 0.16: degree-5 series exact to 1e-5 in the exponent
+          } else if (!__any_sync(0xffffffffu, wm * wm >= cp.wmax)) {
+            exp_block<true>(v, cp, pk);
+          } else {                                        // rare: logits beyond the series' range -> exact tanh for the block
 #pragma unroll
-            for (int i = 0; i < 16; ++i) wm = fmaxf(wm, fabsf(__uint_as_float(v[i])));
-            // The softmax warps are instruction-issue bound (timeline: IPC ~0.9 while computing), so the common case gets the
-            // shortest polynomial: for |z| <= wlo (|z/clamp| <= 0.16) the degree-5 series is exact to 1e-5 in the exponent.
-            if (!__any_sync(0xffffffffu, wm > cp.wlo)) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float z = __uint_as_float(v[i]);
-                const float w = z * z;
-                float q = fmaf(w, cp.c2, cp.c1);
-                q = fmaf(w, q, cp.c0);
-                arg[i] = z * q;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float z = __uint_as_float(v[i]);
-                const float w = z * z;
-                float q = fmaf(w, cp.c4, cp.c3);
-                q = fmaf(w, q, cp.c2);
-                q = fmaf(w, q, cp.c1);
-                q = fmaf(w, q, cp.c0);
-                arg[i] = z * q;
-              }
-              if (__any_sync(0xffffffffu, wm * wm >= cp.wmax)) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const float z = __uint_as_float(v[i]);
-                  if (z * z >= cp.wmax) arg[i] = softclamp_exp2_arg_exact(z, cp.clamp);
-                }
-              }
-            }
-            float p[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) p[i] = ex2_approx(arg[i]);
-            if (c0 + 32 > nvalid) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) p[i] = (c0 + hh * 16 + i < nvalid) ? p[i] : 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pk[i] = 0u;
+            for (int i = 0; i < 16; ++i)
+              pk[i] = pack_bf16(ex2_approx(softclamp_exp2_arg_exact(__uint_as_float(v[2 * i]), cp.ex_a, cp.ex_b)),
+                                ex2_approx(softclamp_exp2_arg_exact(__uint_as_float(v[2 * i + 1]), cp.ex_a, cp.ex_b)));
           }
+          if (c0 + 32 > nvalid) {                          // ragged last tile: keys beyond kv_len contribute exactly zero
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const int chunk = ((cq & 1) * 4 + hh * 2 + q) ^ (r & 7);
-            *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t keep = (c0 + 2 * i + 1 < nvalid) ? 0xffffffffu : (c0 + 2 * i < nvalid) ? 0x0000ffffu : 0u;
+              pk[i] &= keep;
+            }
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((cq & 1) * 4 + q) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
         if (warp == 0 && lane == 0) dbg_stamp(g, 0);
         tc_fence_before();             // this lane's tcgen05.ld of S are complete (tcgen05.wait::ld above)
@@ -480,6 +483,8 @@ extern "C" int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream)
     a.cp.wmax = (float)(0.25 * c2);
     a.cp.clamp = (float)c;
     a.cp.wlo = (float)(0.16 * c);
+    a.cp.ex_a = (float)(2.0 * L2E / c);
+    a.cp.ex_b = (float)(L2E * c);
   }
   const uint64_t q_rows = (uint64_t)d->batch * d->q_rows_per_batch;
   const int kv_batches = d->kv_batch_mod > 0 ? d->kv_batch_mod : d->batch;
