@@ -35,7 +35,10 @@ constexpr int ATT_SK = 2 * 16384;               // ATT_KV x 16 KB  K   [128 keys
 constexpr int ATT_SV = ATT_SK + ATT_KV * 16384; // ATT_KV x 20 KB  V^T 2 x [80 rows, 64 keys]
 constexpr int ATT_SP = ATT_SV + ATT_KV * ATT_VSTAGE; // 2 x 32 KB  P   2 x [128 q, 64 keys]
 constexpr int ATT_BAR = ATT_SP + 2 * 32768;
-constexpr int ATT_SMEM = ATT_BAR + 256;
+constexpr int ATT_LENS = ATT_BAR + 256;          // clamped kv length of every kv sequence of the call
+constexpr int ATT_MAXB = 1024;                  // more kv sequences than this: lengths are read from global memory instead
+constexpr int ATT_SMEM = ATT_LENS + ATT_MAXB * 4;
+static_assert(ATT_SMEM <= 232448, "shared memory budget");
 constexpr uint32_t ATT_TMEM_COLS = 512;         // S0 @0, S1 @128, O0 @256, O1 @336 (80 columns each)
 constexpr uint32_t ATT_TMEM_O = 256;
 
@@ -99,41 +102,63 @@ struct ItemCursor {          // iterates the (item, kv-tile) sequence of this CT
   int it, item, j, nt, b, h, qt, kvb, kv_len;
   bool valid;
 };
-
-__device__ __forceinline__ void cursor_load(ItemCursor& c, const e2b_attn_desc& d, int qtiles, int total) {
+// item = (b * heads + h) * qtiles + qt advances by gridDim.x per step.  The step is decomposed once into mixed-radix digits so
+// that an item switch is a few adds and compares, and the clamped kv lengths of the call sit in shared memory: a timeline
+// showed the direct decode (five integer divisions, each with a MUFU.RCP queued behind the softmax warps' ex2 stream, and a
+// kv_lens global load whose destination register was spilled, i.e. waited for at once) costing ~2K cycles per item.
+struct ItemWalk {
+  ItemCursor c;
+  int dq, dh, db, dkvb;
+  const int* lens;           // shared memory, [kv batches] (null: more than ATT_MAXB sequences, read global memory)
+};
+__device__ __forceinline__ int clamped_kv_len(const e2b_attn_desc& d, int kvb) {
+  const int kv_len = d.kv_lens ? (__ldg(d.kv_lens + kvb) + d.kv_lens_add) : d.kv_rows_per_batch;
+  return max(0, min(kv_len, d.kv_rows_per_batch));
+}
+__device__ __forceinline__ void cursor_fetch(ItemWalk& w, const e2b_attn_desc& d, int total) {
+  ItemCursor& c = w.c;
   c.valid = c.item < total;
-  if (!c.valid) return;
+  c.j = 0;
+  c.kv_len = !c.valid ? 0 : w.lens ? w.lens[c.kvb] : clamped_kv_len(d, c.kvb);
+  c.nt = max(1, (c.kv_len + ATT_BK - 1) / ATT_BK);        // at least one (fully masked) tile so O is defined
+}
+__device__ __forceinline__ void walk_init(ItemWalk& w, const e2b_attn_desc& d, int qtiles, int total, const int* lens) {
+  const int g = gridDim.x;
+  w.dq = g % qtiles;
+  const int gh = g / qtiles;
+  w.dh = gh % d.heads;
+  w.db = gh / d.heads;
+  w.dkvb = d.kv_batch_mod > 0 ? w.db % d.kv_batch_mod : w.db;
+  w.lens = lens;
+  ItemCursor& c = w.c;
+  c.it = 0;
+  c.item = blockIdx.x;
   c.qt = c.item % qtiles;
   const int bh = c.item / qtiles;
   c.h = bh % d.heads;
   c.b = bh / d.heads;
   c.kvb = d.kv_batch_mod > 0 ? c.b % d.kv_batch_mod : c.b;
-  int kv_len = d.kv_lens ? (__ldg(d.kv_lens + c.kvb) + d.kv_lens_add) : d.kv_rows_per_batch;
-  c.kv_len = max(0, min(kv_len, d.kv_rows_per_batch));
-  c.nt = max(1, (c.kv_len + ATT_BK - 1) / ATT_BK);        // at least one (fully masked) tile so O is defined
-  c.j = 0;
-}
-// Every role walks the same item sequence.  `nx` is the successor item, loaded one item early so that the kv_lens
-// global load (and the index arithmetic) is never on the critical path of an item switch.
-struct ItemWalk {
-  ItemCursor c, nx;
-};
-__device__ __forceinline__ void walk_init(ItemWalk& w, const e2b_attn_desc& d, int qtiles, int total) {
-  w.c.it = 0;
-  w.c.item = blockIdx.x;
-  cursor_load(w.c, d, qtiles, total);
-  w.nx = w.c;
-  ++w.nx.it;
-  w.nx.item += gridDim.x;
-  cursor_load(w.nx, d, qtiles, total);
+  cursor_fetch(w, d, total);
 }
 __device__ __forceinline__ void walk_next_item(ItemWalk& w, const e2b_attn_desc& d, int qtiles, int total) {
-  w.c = w.nx;
-  if (w.c.valid) {
-    ++w.nx.it;
-    w.nx.item += gridDim.x;
-    cursor_load(w.nx, d, qtiles, total);
+  ItemCursor& c = w.c;
+  ++c.it;
+  c.item += gridDim.x;
+  int carry = 0;
+  c.qt += w.dq;
+  if (c.qt >= qtiles) { c.qt -= qtiles; carry = 1; }
+  c.h += w.dh + carry;
+  carry = 0;
+  if (c.h >= d.heads) { c.h -= d.heads; carry = 1; }
+  c.b += w.db + carry;
+  if (d.kv_batch_mod > 0) {
+    c.kvb += w.dkvb + carry;
+    if (c.kvb >= d.kv_batch_mod) c.kvb -= d.kv_batch_mod;
+    if (c.kvb >= d.kv_batch_mod) c.kvb -= d.kv_batch_mod;
+  } else {
+    c.kvb = c.b;
   }
+  cursor_fetch(w, d, total);
 }
 __device__ __forceinline__ void walk_next_tile(ItemWalk& w, const e2b_attn_desc& d, int qtiles, int total) {
   if (++w.c.j == w.c.nt) walk_next_item(w, d, qtiles, total);
@@ -194,6 +219,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     tmem_alloc(tmem_slot, ATT_TMEM_COLS);
     tmem_relinquish();
   }
+  int* lens_s = reinterpret_cast<int*>(smem + ATT_LENS);
+  {
+    const int kvb_n = d.kv_batch_mod > 0 ? d.kv_batch_mod : d.batch;
+    if (kvb_n <= ATT_MAXB) {
+      for (int i = threadIdx.x; i < kvb_n; i += ATT_THREADS) lens_s[i] = clamped_kv_len(d, i);
+    } else {
+      lens_s = nullptr;
+    }
+  }
   // rows 64..79 of every V^T atom: row 64 = 1.0 (so column 64 of O accumulates the row sums of the bf16 P the MMA actually
   // used), rows 65..79 = 0.  A whole 128-byte row is constant, so the 128-byte swizzle does not matter.  TMA only ever
   // rewrites rows 0..63.
@@ -219,8 +253,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     // those tiles into L2 (no shared-memory cost), so the real loads are L2 hits.
     constexpr int ATT_PF = 6;
     ItemWalk wc, wpf;
-    walk_init(wc, d, qtiles, total);
-    walk_init(wpf, d, qtiles, total);
+    walk_init(wc, d, qtiles, total, lens_s);
+    walk_init(wpf, d, qtiles, total, lens_s);
     ItemCursor& c = wc.c;
     ItemCursor& pf = wpf.c;
     auto prefetch_tile = [&](const ItemCursor& t) {
@@ -267,7 +301,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     // probe -- ~3K cycles of serial work per tile, which (not the softmax, ~1.9K) set the kernel's pace.
     constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, ATT_BK);
     ItemWalk ws;
-    walk_init(ws, d, qtiles, total);
+    walk_init(ws, d, qtiles, total, lens_s);
     ItemCursor& cs = ws.c;
     for (int gs = 0; cs.valid; ++gs) {
       const int sb = gs & 1, ks = gs % ATT_KV, qb = cs.it & 1;
@@ -296,7 +330,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     // ------------------------------------------------------------ O += P V issuer
     constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, ATT_ON);
     ItemWalk wp;
-    walk_init(wp, d, qtiles, total);
+    walk_init(wp, d, qtiles, total, lens_s);
     ItemCursor& cp = wp.c;
     for (int gp = 0; cp.valid; ++gp) {
       const int pb = gp & 1, ks = gp % ATT_KV, ob = cp.it & 1;
@@ -336,7 +370,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     // P: keys c0..c0+31 live in swizzle atom (cq >> 1), 16-byte chunks ((cq & 1) * 4 + q) ^ (r & 7) of the 128-byte row
     const uint32_t p_off = (cq >> 1) * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
     ItemWalk wk;
-    walk_init(wk, d, qtiles, total);
+    walk_init(wk, d, qtiles, total, lens_s);
     ItemCursor& c = wk.c;
     // Deferred item epilogue: O of item i is read out after the FIRST tile of item i+1, when its last PV has long completed,
     // so the o_full wait and the stores are off the critical path (O and Q are double-buffered across items).
