@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(2 * DW_C, 2) dwconv_tma_kernel(const __grid_co
   const int tid = threadIdx.x & (DW_C - 1);       // channel inside the tile
   const int rhalf = threadIdx.x / DW_C;           // which 32-row half of the tile this thread produces
   const int cchunks = (C + DW_C - 1) / DW_C, rtiles = (N + DW_T - 1) / DW_T;
-  const int total = batch * rtiles * cchunks;
+  const int per_chunk = batch * rtiles;           // tiles of one channel chunk: chunk-major order, so a CTA keeps its taps
+  const int total = per_chunk * cchunks;
   if (threadIdx.x == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(2 * DW_C, 2) dwconv_tma_kernel(const __grid_co
   }
   __syncthreads();
   auto issue = [&](int tile, int s) {
-    const int cc = tile % cchunks, rt = (tile / cchunks) % rtiles, b = tile / (cchunks * rtiles);
+    const int cc = tile / per_chunk, rem = tile - cc * per_chunk, b = rem / rtiles, rt = rem - b * rtiles;
     mbar_arrive_expect_tx(&full[s], ROWS * DW_C * 4);
     tma_load_3d(buf + (size_t)s * ROWS * DW_C, &tmx, &full[s], cc * DW_C, rt * DW_T - HALF, b);
   };
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(2 * DW_C, 2) dwconv_tma_kernel(const __grid_co
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
     const int s = it & 1;
     if (threadIdx.x == 0 && tile + (int)gridDim.x < total) issue(tile + gridDim.x, s ^ 1);
-    const int cc = tile % cchunks, rt = (tile / cchunks) % rtiles, b = tile / (cchunks * rtiles);
+    const int cc = tile / per_chunk, rem = tile - cc * per_chunk, b = rem / rtiles, rt = rem - b * rtiles;
     const int c = cc * DW_C + tid;
     const int r0 = rt * DW_T;
     const int len = lens ? min(N, __ldg(lens + b)) : N;
