@@ -146,6 +146,17 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def _load_traffic():
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')) as f:
+            return json.load(f)
+    except OSError:
+        return {}
+
+
+NCU_TRAFFIC = _load_traffic()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -253,9 +264,21 @@ def main():
         top = max(rows, key=lambda r: r['ms'])
         per_launch_ms = top['ms'] / top['count']
         achieved = top['flops'] / (per_launch_ms * 1e-3) / 1e12
-        roof = dict(bound='tensor', kernel=f"{top['kind']} M={top['m']} N={top['n']} K={top['k']}", achieved=achieved, peak=pk['burst'],
-                    unit='TFLOP/s', frac=achieved / pk['burst'], peak_source=f"{pk['src']} burst bf16 (MEASURED_PEAKS.json)",
-                    launches_per_update=top['count'], ms_per_launch=per_launch_ms, share_of_step=top['ms'] / total_ms, traffic=None)
+        def roof_of(r):
+            ms_l = r['ms'] / r['count']
+            ach = r['flops'] / (ms_l * 1e-3) / 1e12
+            key = f"{r['kind']} M={r['m']} N={r['n']} K={r['k']}"
+            tr = NCU_TRAFFIC.get(key)             # dram bytes per launch from the committed ncu --set full capture (or None)
+            return dict(bound='tensor', kernel=key, achieved=ach, peak=pk['burst'], unit='TFLOP/s', frac=ach / pk['burst'],
+                        peak_source=f"{pk['src']} burst bf16 (MEASURED_PEAKS.json)", launches_per_update=r['count'], ms_per_launch=ms_l,
+                        share_of_step=r['ms'] / total_ms, algorithmic_bytes=r['bytes'],
+                        traffic=tr['dram_bytes_per_launch'] if tr else None, traffic_source=tr['source'] if tr else None)
+        roof = roof_of(top)
+        if top['kind'] == 'attention':
+            # the attention kernel's binding unit is the MUFU pipe (one ex2 per logit at 16 / clk / SM = 1024 clk per 128x128 tile
+            # against 512 clk of MMA for head dim 64), so its tensor-pipe fraction cannot exceed ~0.5 (profiles/r01_pipe_microbench.txt)
+            roof['note'] = 'MUFU-bound kernel (ex2 16/clk/SM): tensor fraction ceiling ~0.5 at head dim 64'
+            roof['top_gemm'] = roof_of(max((r for r in rows if r['kind'].startswith('gemm')), key=lambda r: r['ms']))
         flops_update = eng.flops_per_forward()                   # both passes, as executed
         tf_all = flops_update / (total_ms * 1e-3) / 1e12
         by_kind = {}
