@@ -22,8 +22,11 @@ __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __e
 // ------------------------------------------------------------------------------------------------ rmsnorm
 constexpr int NORM_MAX_V4 = 16;   // C <= 2048
 
-template <int OUT_MODE>   // 0 bf16, 1 fp32, 2 bf16 (hi, lo) pair with lo at column + C
-__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, int ldx, void* __restrict__ yv, int ldy,
+// NV4 = float4 per lane the row may need (C <= 128 NV4): sizing the register tile to the row (8 for C = 1024, 10 for 1280, 4 for
+// 512) instead of the maximum keeps the kernel at <= 64 registers, i.e. 32 resident warps per SM instead of 16 -- the kernel
+// is latency bound (ncu: DRAM 60-68 %, long-scoreboard 6.5-7.7 stalls per issue), so bytes in flight are what it needs.
+template <int OUT_MODE, int NV4>   // OUT_MODE: 0 bf16, 1 fp32, 2 bf16 (hi, lo) pair with lo at column + C
+__global__ void __launch_bounds__(256, NV4 <= 10 ? 4 : 2) rmsnorm_kernel(const float* __restrict__ x, int ldx, void* __restrict__ yv, int ldy,
                                                       const float* __restrict__ scale, int scale_bstride, int rows_out_total,
                                                       int rows_per_batch, int skip_rows, int C, float sqrt_c) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -32,10 +35,10 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
   const int b = warp / rpo, i = warp % rpo;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(b * rows_per_batch + skip_rows + i) * ldx);
   const int nv = C >> 2;
-  float4 v[NORM_MAX_V4];
+  float4 v[NV4];
   float ss = 0.f;
 #pragma unroll
-  for (int k = 0; k < NORM_MAX_V4; ++k) {
+  for (int k = 0; k < NV4; ++k) {
     const int idx = lane + 32 * k;
     if (idx < nv) {
       v[k] = xr[idx];
@@ -46,7 +49,7 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
   const float inv = sqrt_c / fmaxf(sqrtf(ss), 1e-12f);
   const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * scale_bstride);
 #pragma unroll
-  for (int k = 0; k < NORM_MAX_V4; ++k) {
+  for (int k = 0; k < NV4; ++k) {
     const int idx = lane + 32 * k;
     if (idx < nv) {
       const float4 s = __ldg(sc + idx);
@@ -401,9 +404,21 @@ extern "C" int e2b_rmsnorm_launch(const float* x, int ldx, void* y, int ldy, con
   const int blocks = (rows_out + 7) / 8;
   ProfScope ps(stream, "rmsnorm", rows_out, C, 0, 3.0 * rows_out * C, (double)rows_out * C * (out_mode == 1 ? 8.0 : (out_mode == 2 ? 8.0 : 6.0)));
   const float sq = sqrtf((float)C);
-  if (out_mode == 1) rmsnorm_kernel<1><<<blocks, 256, 0, stream>>>(x, ldx, y, ldy, scale, scale_bstride, rows_out, rows_per_batch, skip_rows, C, sq);
-  else if (out_mode == 2) rmsnorm_kernel<2><<<blocks, 256, 0, stream>>>(x, ldx, y, ldy, scale, scale_bstride, rows_out, rows_per_batch, skip_rows, C, sq);
-  else rmsnorm_kernel<0><<<blocks, 256, 0, stream>>>(x, ldx, y, ldy, scale, scale_bstride, rows_out, rows_per_batch, skip_rows, C, sq);
+  const int nv4 = (C / 4 + 31) / 32;
+#define E2B_NORM_LAUNCH(MODE_, NV_) \
+  rmsnorm_kernel<MODE_, NV_><<<blocks, 256, 0, stream>>>(x, ldx, y, ldy, scale, scale_bstride, rows_out, rows_per_batch, skip_rows, C, sq)
+#define E2B_NORM_MODE(MODE_)                      \
+  do {                                            \
+    if (nv4 <= 4) E2B_NORM_LAUNCH(MODE_, 4);      \
+    else if (nv4 <= 8) E2B_NORM_LAUNCH(MODE_, 8); \
+    else if (nv4 <= 10) E2B_NORM_LAUNCH(MODE_, 10); \
+    else E2B_NORM_LAUNCH(MODE_, NORM_MAX_V4);     \
+  } while (0)
+  if (out_mode == 1) E2B_NORM_MODE(1);
+  else if (out_mode == 2) E2B_NORM_MODE(2);
+  else E2B_NORM_MODE(0);
+#undef E2B_NORM_MODE
+#undef E2B_NORM_LAUNCH
   return check_launch("rmsnorm");
 }
 
