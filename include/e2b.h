@@ -16,6 +16,8 @@
  *                                   X3:2090-2113, 162-173, 2255
  *   e2b_sample                      the odeint loop of E2TTS.sample                      X3:2221-2256
  *   e2b_melspec                     MelSpec.forward                                      X3:375-417
+ *   e2b_stage_clip                  E2TTS.encode_video with a feature cache present: nearest-video-frame resampling of the
+ *                                   cached CLIP embeddings to the latent frame rate, zero padding           X3:1802-1826
  */
 #ifndef E2B_H_
 #define E2B_H_
@@ -86,6 +88,13 @@ int e2b_guided_euler(float* y_dev, const float* pred_dev, int P, int B, long lon
  * arrays: window[n_fft], fb[n_fft/2+1, n_mels] (torchaudio melscale_fbanks layout). */
 int e2b_melspec(const float* wav_dev, int B, int nw, int n_fft, int hop, int n_mels, const float* window_dev,
                 const float* fb_dev, float* out_dev, e2b_stream stream);
+
+/* Condition staging: out_dev [B,l,d] fp32 = for every clip b and latent frame k < count_b the cached embedding row
+ *   j = min(round_half_even((start_b + k*frame_size + frame_size/2) / sampling_rate / (duration_b / (F_b - 1))), F_b - 1)
+ * (double arithmetic, the reference's operation order), zeros for k >= count_b.  emb_dev: all clips' embeddings back to back
+ * [sum F_b, d] fp32; meta_dev [B,4] int64 = {row offset, F_b, count_b, start_sample_b}; duration_dev [B] double (seconds). */
+int e2b_stage_clip(const float* emb_dev, const long long* meta_dev, const double* duration_dev, int B, int l, int d,
+                   int sampling_rate, int frame_size, float* out_dev, e2b_stream stream);
 
 /* algorithmic FLOPs of one e2b_forward at the prepared shape as executed (skipped null-pass attn2 not counted) */
 double e2b_forward_flops(e2b_handle* h);

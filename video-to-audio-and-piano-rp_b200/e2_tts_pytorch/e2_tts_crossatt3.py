@@ -17,9 +17,11 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from pathlib import Path
 from typing import Callable
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -518,9 +520,65 @@ class E2TTS(Module):
             hidden = self.text_encoder2(input_ids=ids, attention_mask=am)[0]
         return hidden, (am == 1)
 
+    VIDEO_FEATURE_SUFFIX = {'clip_vit': '.generated.npz', 'clip_vit2': '.generated.clip_vit2.npz', 'clip_convnext': '.generated.clip_convnext.npz',
+                            'dinov2': '.generated.dinov2.npz', 'mixed': '.generated.mixed.npz'}
+
+    def video_feature_path(self, video_path):
+        """Cache file of a clip's per-video-frame embeddings (X3:1692-1704)."""
+        if self.video_encoder not in self.VIDEO_FEATURE_SUFFIX:
+            raise Exception('Invalid video_encoder ' + str(self.video_encoder))
+        return video_path.replace('.mp4', self.VIDEO_FEATURE_SUFFIX[self.video_encoder])
+
     def encode_video(self, video_paths, l):
-        raise NotImplementedError('CLIP feature extraction from video files is outside the hot path (SURVEY.md 8f N2): '
-                                  'pass the per-frame CLIP stream as text=Float[b, n, dim_text]')
+        """Per-latent-frame CLIP stream Float[b, l, d] from the reference's feature caches (X3:1659-1827).
+
+        Each entry of `video_paths` is None (all-zero clip), a path, or (path, start_sample, max_sample).  The cache is the
+        `.npz` the reference writes next to the video (arr_0 = embeddings [F, d] fp32, arr_1 = duration in seconds, X3:1796);
+        running the CLIP image encoder itself is out of scope, so a missing cache is an error here.  The nearest-video-frame
+        resampling and the zero padding run on the GPU (csrc/staging.cu)."""
+        d = self.dim_text if self.proj_text is None else self.dim_text_raw
+        device = self.device
+        if torch.device(device).type != 'cuda':
+            raise RuntimeError('E2TTS.encode_video stages on CUDA only: libe2b has no CPU path')
+        embs, meta, durs = [], [], []
+        off = 0
+        for video_path in video_paths:
+            if video_path is None:                                                   # X3:1670-1673
+                meta.append((0, 2, 0, 0))
+                durs.append(1.0)
+                continue
+            if isinstance(video_path, tuple):                                        # X3:1675-1678
+                video_path, start_sample, max_sample = video_path
+            else:
+                start_sample, max_sample = 0, None
+            feature_path = self.video_feature_path(video_path)
+            if not os.path.exists(feature_path):
+                raise RuntimeError(f'no cached video features at {feature_path}: extracting them (CLIP image encoder) is outside the '
+                                   'hot path -- run the reference once to create the cache, or pass text=Float[b, n, dim_text]')
+            data = np.load(feature_path)
+            emb = np.ascontiguousarray(data['arr_0'], dtype=np.float32)
+            duration = float(data['arr_1'].item())
+            if emb.ndim != 2 or emb.shape[1] != d:
+                raise RuntimeError(f'{feature_path}: expected embeddings [F, {d}], got {tuple(emb.shape)}')
+            if emb.shape[0] < 2:
+                raise ZeroDivisionError('float division by zero')                    # duration / (F - 1), X3:1806
+            if max_sample is None:
+                max_sample = int(duration * self.sampling_rate)                      # X3:1802-1803
+            count = min(l, len(range(start_sample, max_sample, self.frame_size)))     # X3:1805-1810
+            if count == 0:
+                raise RuntimeError('torch.cat(): expected a non-empty list of Tensors')   # what X3:1811 raises
+            embs.append(torch.from_numpy(emb))
+            meta.append((off, emb.shape[0], count, start_sample))
+            durs.append(duration)
+            off += emb.shape[0]
+        out = torch.empty(len(video_paths), l, d, device=device, dtype=torch.float32)
+        emb_dev = (torch.cat(embs, 0) if embs else torch.zeros(2, d)).to(device, non_blocking=True)
+        meta_dev = torch.tensor(meta, dtype=torch.int64).to(device, non_blocking=True)
+        dur_dev = torch.tensor(durs, dtype=torch.float64).to(device, non_blocking=True)
+        rc = _lib.lib().e2b_stage_clip(_lib.ptr(emb_dev), _lib.ptr(meta_dev), _lib.ptr(dur_dev), len(video_paths), l, d,
+                                       int(self.sampling_rate), int(self.frame_size), _lib.ptr(out), _lib.stream_ptr())
+        _lib.check(rc, None, 'e2b_stage_clip')
+        return out
 
     def encode_frames(self, x, l):
         """5-frame sliding windows -> Video2RollNet -> sigmoid -> x3 repeat -> cut/pad to l (X3:1525-1555)."""
