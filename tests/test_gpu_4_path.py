@@ -146,3 +146,33 @@ def test_size_independent_properties_batch64():
     assert torch.isfinite(full).all()
     assert torch.equal(full[2:5], sub)
     assert not torch.equal(full[0], full[1])
+
+
+@pytest.mark.parametrize('apg', [False, True])
+def test_graph_replay_is_bit_identical_to_eager(apg):
+    """e2b_sample runs eagerly on a first call, captures a CUDA graph of the whole step loop on the second call with the same
+    signature and replays it afterwards: all three must agree bit for bit, also when the conditions change between calls."""
+    g, r, cfg, bt = load_gold('tiny_x3.pt')
+    m, _ = build_model(cfg, r['weight_seed'])
+    d = dev(bt)
+
+    def run(y0, clip):
+        return m.sample(torch.zeros_like(y0), text=clip, lens=d['lens'], duration=d['lens'], steps=r['steps'],
+                        cfg_strength=r['cfg_strength'], remove_parallel_component=apg, sway_sampling=True, return_raw_output=True,
+                        context=d['ctx'], context_mask=d['ctx_mask'], frames=d['frames'], noise=y0)
+
+    eager = run(d['y0'], d['clip'])
+    l_eager = m._last_launches
+    captured = run(d['y0'].clone(), d['clip'])
+    replayed = run(d['y0'].clone(), d['clip'])
+    assert torch.equal(eager, captured) and torch.equal(eager, replayed)
+    assert m._last_launches == l_eager                     # replay reports the launches of the captured sequence
+    # new data through the same graph
+    y1, clip1 = torch.randn_like(d['y0']), torch.randn_like(d['clip'])
+    via_graph = run(y1, clip1)
+    # a different signature (other step count) goes back to the eager path; then compare the new data eagerly
+    m.sample(torch.zeros_like(y1), text=clip1, lens=d['lens'], duration=d['lens'], steps=r['steps'] + 1, cfg_strength=r['cfg_strength'],
+             remove_parallel_component=apg, return_raw_output=True, context=d['ctx'], context_mask=d['ctx_mask'], frames=d['frames'], noise=y1)
+    eager1 = run(y1, clip1)                                # first sighting after the signature changed: eager again
+    assert torch.equal(via_graph, eager1)
+    assert not torch.equal(via_graph, eager)

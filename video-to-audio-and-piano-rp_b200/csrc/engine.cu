@@ -4,6 +4,7 @@
 //   text -> frames -> cross-condition -> U-Net skip -> conv -> self-attn -> cross-attn(T5) -> GEGLU FF.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -11,6 +12,7 @@
 
 #include "../../include/e2b.h"
 #include "kernels.h"
+#include "prof.h"
 
 typedef __nv_bfloat16 bf16;
 
@@ -40,6 +42,16 @@ struct e2b_handle {
   std::string err;
   long long launches = 0;
 
+  // CUDA graph of the whole e2b_sample step loop (all Euler updates: ~380 launches each).  The eager path stays the default
+  // for a first call; a second call with the same signature (shapes, grid, guidance, pass flags, state pointer) is captured on
+  // the library's own stream and replayed from then on.  E2B_GRAPH=0 disables it.
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t gev0 = nullptr, gev1 = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  std::vector<unsigned char> gkey, gcand;
+  long long glaunches = 0;
+  int epoch = 0;                   // bumped whenever buffers are (re)allocated: invalidates the graph
+
   // global weights
   float *registers = nullptr, *t_registers = nullptr, *f_registers = nullptr, *abs_pos = nullptr, *final_g = nullptr;
   float *fourier_w = nullptr, *time_w1 = nullptr, *time_b1 = nullptr;
@@ -63,6 +75,7 @@ struct e2b_handle {
   std::vector<bf16*> skipb, k2, vt2;
   float *qkf = nullptr, *vf = nullptr;      // fp32 q/k and v (fp32 mode)
   std::vector<float*> k2f, v2f;
+  float* ystate = nullptr;         // the ODE state the captured graph works on (the caller's y is copied in and out)
   float *hg = nullptr, *fr0 = nullptr, *clip = nullptr, *pred = nullptr, *gam = nullptr, *tcond = nullptr, *times_dev = nullptr;
   double* apg_scratch = nullptr;
   int *lens_dev = nullptr, *ctx_lens_dev = nullptr;
@@ -592,8 +605,20 @@ extern "C" int e2b_create(const e2b_config* cfg, e2b_handle** out) {
   return 0;
 }
 
+static void drop_graph(e2b_handle* h) {
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
+  h->gexec = nullptr;
+  h->gkey.clear();
+  h->gcand.clear();
+  ++h->epoch;
+}
+
 extern "C" void e2b_destroy(e2b_handle* h) {
   if (!h) return;
+  drop_graph(h);
+  if (h->gstream) cudaStreamDestroy(h->gstream);
+  if (h->gev0) cudaEventDestroy(h->gev0);
+  if (h->gev1) cudaEventDestroy(h->gev1);
   free_workspace(h);
   free_pool(h->wallocs);
   delete h;
@@ -607,6 +632,7 @@ extern "C" int e2b_load_weights(e2b_handle* h, const e2b_tensor* tensors, int n,
   const e2b_config& c = h->cfg;
   free_pool(h->wallocs);
   h->weights_loaded = false;
+  drop_graph(h);
   WMap w;
   for (int i = 0; i < n; ++i) w.m[tensors[i].name] = &tensors[i];
   const std::string T = "transformer.";
@@ -700,6 +726,7 @@ extern "C" int e2b_prepare(e2b_handle* h, int B, int n, int nc, int P) {
   if (B <= 0 || n <= 0 || nc <= 0 || P < 1 || P > 8) return fail(h, "e2b_prepare: bad shape B=%d n=%d nc=%d P=%d", B, n, nc, P);
   if (n > c.max_seq_len) return fail(h, "e2b_prepare: n=%d exceeds max_seq_len=%d", n, c.max_seq_len);   // X3:958
   if (B == h->B && n == h->n && nc == h->nc && P == h->P) return 0;
+  drop_graph(h);
   free_workspace(h);
   h->B = B; h->n = n; h->nc = nc; h->P = P; h->Pctx = P;
   h->N = n + c.num_registers; h->Bt = B * P; h->M = (size_t)h->Bt * h->N;
@@ -752,6 +779,7 @@ extern "C" int e2b_prepare(e2b_handle* h, int B, int n, int nc, int P) {
   DA(h->sallocs, h->fr0, M * df);
   DA(h->sallocs, h->clip, (size_t)B * n * dt);
   DA(h->sallocs, h->pred, (size_t)h->Bt * n * c.num_channels);
+  DA(h->sallocs, h->ystate, (size_t)B * n * c.num_channels);
   h->gam_capacity = std::max(1024, h->Bt);
   DA(h->sallocs, h->gam, (size_t)h->gam_capacity * h->nmat * dim);
   DA(h->sallocs, h->tcond, (size_t)h->gam_capacity * dim);
@@ -829,19 +857,12 @@ extern "C" int e2b_forward(e2b_handle* h, const float* x_dev, float t, float* pr
   return pred_head(h, pred_dev, st);
 }
 
-extern "C" int e2b_sample(e2b_handle* h, float* y_dev, const float* t_grid_host, int steps, const float* guidance_w_host, int apg,
-                          float keep_parallel, e2b_stream stream) {
-  if (!h) return fail(h, "null handle");
-  if (!h->conditions_set) return fail(h, "e2b_sample: call e2b_set_conditions first");
-  if (steps < 1) return fail(h, "e2b_sample: steps must be >= 1");
-  if (steps - 1 > h->gam_capacity) return fail(h, "e2b_sample: too many steps");
-  if (h->P > 1 && !guidance_w_host) return fail(h, "e2b_sample: guidance weights required");
-  cudaStream_t st = (cudaStream_t)stream;
+// the step loop of e2b_sample (time tables already computed)
+static int run_sample_steps(e2b_handle* h, float* y_dev, const float* t_grid_host, int steps, const float* guidance_w_host, int apg,
+                            float keep_parallel, cudaStream_t st) {
   const e2b_config& c = h->cfg;
   const size_t per_pass = (size_t)h->B * h->n;
   const long long per_sample = (long long)h->n * c.num_channels;
-  if (steps == 1) return 0;
-  if (compute_time_tables(h, t_grid_host, steps - 1, st)) return -1;
   for (int p = 0; p < h->P; ++p)
     if (cast_act(h, y_dev, c.num_channels, h->ybf + p * per_pass * ldb(h, c.num_channels), c.num_channels, c.num_channels, per_pass, st)) return -1;
   for (int s = 0; s < steps - 1; ++s) {
@@ -857,6 +878,75 @@ extern "C" int e2b_sample(e2b_handle* h, float* y_dev, const float* t_grid_host,
       for (int p = 0; p < h->P; ++p)
         if (cast_act(h, y_dev, c.num_channels, h->ybf + p * per_pass * ldb(h, c.num_channels), c.num_channels, c.num_channels, per_pass, st)) return -1;
   }
+  return 0;
+}
+
+static bool graphs_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("E2B_GRAPH");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+extern "C" int e2b_sample(e2b_handle* h, float* y_dev, const float* t_grid_host, int steps, const float* guidance_w_host, int apg,
+                          float keep_parallel, e2b_stream stream) {
+  if (!h) return fail(h, "null handle");
+  if (!h->conditions_set) return fail(h, "e2b_sample: call e2b_set_conditions first");
+  if (steps < 1) return fail(h, "e2b_sample: steps must be >= 1");
+  if (steps - 1 > h->gam_capacity) return fail(h, "e2b_sample: too many steps");
+  if (h->P > 1 && !guidance_w_host) return fail(h, "e2b_sample: guidance weights required");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (steps == 1) return 0;
+  if (compute_time_tables(h, t_grid_host, steps - 1, st)) return -1;      // host -> device copy of the grid: outside the graph
+  if (!graphs_enabled() || e2b_prof_is_on_()) return run_sample_steps(h, y_dev, t_grid_host, steps, guidance_w_host, apg, keep_parallel, st);
+
+  // signature of everything that shapes the launch sequence or is baked into kernel parameters
+  std::vector<unsigned char> key;
+  auto put = [&](const void* p, size_t n) { key.insert(key.end(), (const unsigned char*)p, (const unsigned char*)p + n); };
+  put(&steps, sizeof steps); put(&apg, sizeof apg); put(&keep_parallel, sizeof keep_parallel);
+  put(&h->epoch, sizeof h->epoch); put(&h->P, sizeof h->P); put(h->pass_flags, sizeof(int) * h->P);
+  put(t_grid_host, sizeof(float) * steps);
+  if (h->P > 1) put(guidance_w_host, sizeof(float) * (h->P - 1));
+
+  if (!h->gexec || key != h->gkey) {
+    if (key != h->gcand) {                     // first sighting: run eagerly (this also performs every one-time kernel setup)
+      h->gcand = key;
+      return run_sample_steps(h, y_dev, t_grid_host, steps, guidance_w_host, apg, keep_parallel, st);
+    }
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; h->gkey.clear(); }
+    if (!h->gstream) {
+      CU(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&h->gev0, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&h->gev1, cudaEventDisableTiming));
+    }
+    const long long l0 = h->launches;
+    CU(cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_sample_steps(h, h->ystate, t_grid_host, steps, guidance_w_host, apg, keep_parallel, h->gstream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->gstream, &graph);
+    h->glaunches = h->launches - l0;
+    h->launches = l0;
+    if (rc != 0 || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      if (rc != 0) return -1;
+      return fail(h, "e2b_sample: graph capture failed: %s", cudaGetErrorString(ce));
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&h->gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { h->gexec = nullptr; return fail(h, "e2b_sample: graph instantiation failed: %s", cudaGetErrorString(ie)); }
+    h->gkey = key;
+  }
+  // run the graph on the library's stream, ordered after / before the caller's stream
+  const size_t ybytes = (size_t)h->B * h->n * h->cfg.num_channels * sizeof(float);
+  CU(cudaMemcpyAsync(h->ystate, y_dev, ybytes, cudaMemcpyDeviceToDevice, st));
+  CU(cudaEventRecord(h->gev0, st));
+  CU(cudaStreamWaitEvent(h->gstream, h->gev0, 0));
+  CU(cudaGraphLaunch(h->gexec, h->gstream));
+  CU(cudaEventRecord(h->gev1, h->gstream));
+  CU(cudaStreamWaitEvent(st, h->gev1, 0));
+  CU(cudaMemcpyAsync(y_dev, h->ystate, ybytes, cudaMemcpyDeviceToDevice, st));
+  h->launches += h->glaunches;
   return 0;
 }
 

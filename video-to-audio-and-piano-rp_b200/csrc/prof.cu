@@ -35,6 +35,8 @@ ProfScope::~ProfScope() {
 
 using namespace e2b;
 
+extern "C" bool e2b_prof_is_on_() { return e2b::g_on; }
+
 extern "C" void e2b_prof_enable(int on) {
   for (auto& r : g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   g_recs.clear();

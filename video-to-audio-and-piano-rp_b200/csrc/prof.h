@@ -14,6 +14,7 @@ struct ProfScope {
 
 extern "C" {
 void e2b_prof_enable(int on);                       // clears previous records
+bool e2b_prof_is_on_();                             // (events cannot be recorded inside a graph capture)
 // Writes lines "kind m n k count total_ms flops_per_launch bytes_per_launch\n" into buf; returns bytes needed.
 int e2b_prof_report(char* buf, int buflen);
 }
