@@ -619,7 +619,16 @@ extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
   }
   if (k != d->K) { e2b_set_kernel_error("gemm: sum(ka)=%d != K=%d", k, d->K); return -1; }
   // Narrow outputs use 128-wide tiles; GEGLU needs the 128+128 packed 256 tile.
-  const bool bn256 = (d->epi == E2B_EPI_GEGLU) || (d->N % 256 == 0) || (d->N > 1024);
+  bool bn256 = (d->epi == E2B_EPI_GEGLU) || (d->N % 256 == 0) || (d->N > 1024);
+  if (bn256 && d->epi != E2B_EPI_GEGLU) {
+    // Few rows (one clip per call): when even the 128x128 tiling fits in one wave, the 128x256 tiling leaves most SMs idle
+    // (single 10 s clip: 52 tiles for 148 SMs at N = 1024) -- take the narrower tile (sample() latency 190 -> 166 ms).
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long mt = (d->M + BM - 1) / BM;
+    if (mt * ((d->N + 127) / 128) <= sms) bn256 = false;
+  }
   if (d->epi == E2B_EPI_GEGLU && d->N % 256) { e2b_set_kernel_error("gemm: GEGLU needs N %% 256 == 0 (N=%d)", d->N); return -1; }
   if (d->epi != E2B_EPI_QKV && (d->N % 4 || d->ldo % 4 || (d->out_b16 && d->ldo_b16 % 4) || (d->resid && d->ldr % 4) || (d->add_table && d->ld_add % 4) ||
                                 (d->gate && d->gate_bstride % 4))) {
