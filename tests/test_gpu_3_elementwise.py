@@ -16,7 +16,7 @@ sp = _lib.stream_ptr
 P = _lib.ptr
 
 
-@pytest.mark.parametrize('C_', [64, 192, 512, 1024, 1280])
+@pytest.mark.parametrize('C_', [64, 192, 512, 1024, 1280, 2048])
 def test_rmsnorm(C_):
     B, N, skip = 3, 37, 5
     x = torch.randn(B * N, C_, device=DEV) * 3
