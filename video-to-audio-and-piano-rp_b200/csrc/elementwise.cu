@@ -17,7 +17,8 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// x * sigmoid(x) as two MUFU ops and three FMA-pipe ops, branch-free (__fdividef carries a range check per call)
+__device__ __forceinline__ float silu(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 
 // ------------------------------------------------------------------------------------------------ rmsnorm
 constexpr int NORM_MAX_V4 = 16;   // C <= 2048
@@ -102,7 +103,7 @@ __device__ __forceinline__ void dwconv_rows(const float* __restrict__ xs, float*
   float win[HALO + DW_G];
 #pragma unroll
   for (int j = 0; j < HALO; ++j) win[j] = ldx(j);
-#pragma unroll 1
+#pragma unroll
   for (int g = 0; g < DW_T / 2; g += DW_G) {
     if (!FULL && out0 + g >= N) break;
 #pragma unroll
