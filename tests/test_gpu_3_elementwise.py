@@ -136,3 +136,45 @@ def test_melspec_vs_torchaudio():
     ref = ref_mod(wav).clamp(min=1e-5).log()
     assert ours.shape == ref.shape
     assert (ours - ref).abs().max().item() < 2e-3 and rel(ours, ref) < 1e-4
+
+
+def _guarded(shape, dtype=torch.float32, pad=4096):
+    """A tensor carved out of a larger sentinel-filled buffer, to catch writes outside the output."""
+    n = 1
+    for s in shape:
+        n *= s
+    raw = torch.full((n + 2 * pad,), 12345.0, device=DEV, dtype=dtype)
+    return raw, raw[pad:pad + n].view(*shape), pad
+
+
+def _guards_intact(raw, pad):
+    return bool((raw[:pad] == 12345.0).all() and (raw[-pad:] == 12345.0).all())
+
+
+@pytest.mark.parametrize('B,N,C_', [(2, 83, 192), (3, 782, 64), (1, 65, 1280)])
+def test_elementwise_kernels_stay_inside_their_outputs(B, N, C_):
+    """No compute-sanitizer on this pool: every element-wise kernel writes into a guarded buffer instead."""
+    lens = torch.tensor([N - 3 * b for b in range(B)], device=DEV, dtype=torch.int32)
+    x = torch.randn(B, N, C_, device=DEV)
+    # dwconv
+    raw, y, pad = _guarded((B, N, C_))
+    wt = (torch.randn(31, C_, device=DEV) / 5).contiguous()
+    kcheck(L().e2b_dwconv_launch(P(x), P(y), P(wt), P(torch.randn(C_, device=DEV)), P(lens), B, N, C_, 31, sp()))
+    torch.cuda.synchronize()
+    assert _guards_intact(raw, pad) and torch.isfinite(y).all()
+    # rmsnorm, bf16 and fp32 outputs, with skipped leading rows
+    scale = torch.rand(B, C_, device=DEV) + 0.5
+    for mode, dt in ((0, torch.bfloat16), (1, torch.float32)):
+        raw, yn, pad = _guarded((B * (N - 5), C_), dt)
+        kcheck(L().e2b_rmsnorm_launch(P(x), C_, P(yn), C_, P(scale), C_, B, N, 5, C_, mode, sp()))
+        torch.cuda.synchronize()
+        assert _guards_intact(raw, pad) and torch.isfinite(yn.float()).all()
+    # condition staging
+    F_ = 17
+    emb = torch.randn(B * F_, 1280, device=DEV)
+    meta = torch.tensor([(b * F_, F_, max(1, N - 7 * b), 0) for b in range(B)], dtype=torch.int64, device=DEV)
+    dur = torch.full((B,), 3.3, dtype=torch.float64, device=DEV)
+    raw, out, pad = _guarded((B, N, 1280))
+    kcheck(L().e2b_stage_clip(P(emb), P(meta), P(dur), B, N, 1280, 24000, 320, P(out), sp()))
+    torch.cuda.synchronize()
+    assert _guards_intact(raw, pad) and torch.isfinite(out).all()
