@@ -97,3 +97,42 @@ def test_mel_filterbank_matches_torchaudio():
     from e2_tts_pytorch.e2_tts_crossatt3 import MelSpec
     ref = torchaudio.functional.melscale_fbanks(513, 0., 12000., 100, 24000, norm=None, mel_scale='htk')
     assert torch.allclose(MelSpec.mel_filterbank(513, 0., 12000., 100, 24000), ref, atol=1e-6)
+
+
+def test_prompt_context_is_encoded_once_per_distinct_prompt():
+    """encode_text_cached: distinct prompts are encoded once, repeated calls hit the cache, and the assembled
+    batch equals the jointly encoded, right-padded batch on every valid token."""
+    import torch
+    from oracle import synth
+    from e2_tts_pytorch.e2_tts_crossatt3 import E2TTS
+    cfg = synth.TINY
+    tr = dict(depth=cfg['depth'], dim=cfg['dim'], dim_text=cfg['dim_text'], dim_frames=cfg['dim_frames'], heads=cfg['heads'], dim_head=64,
+              max_seq_len=cfg['max_seq_len'], if_text_modules=True, if_cross_attn=True, if_audio_conv=True, if_text_conv=True)
+    m = E2TTS(duration_predictor=None, transformer=tr, tokenizer='char_utf8', audiocond_drop_prob=1.1, cond_drop_prob=-0.1,
+              prompt_drop_prob=-0.1, if_cond_proj_in=False, if_embed_text=False, if_text_encoder2=False, if_clip_encoder=False,
+              num_channels=cfg['num_channels'], sampling_rate=24000)
+    calls = []
+
+    def fake_encode_text(prompts):                       # stands in for the frozen T5: one row per word, value = word hash
+        calls.append(list(prompts))
+        toks = [[float(sum(map(ord, w))) for w in p.split()] for p in prompts]
+        nc = max(map(len, toks))
+        hidden = torch.zeros(len(prompts), nc, cfg['dim'])
+        mask = torch.zeros(len(prompts), nc, dtype=torch.bool)
+        for i, t in enumerate(toks):
+            hidden[i, :len(t)] = torch.tensor(t)[:, None] + torch.arange(cfg['dim'])[None, :]
+            hidden[i, len(t):] = -7.0                    # garbage in the padded positions, as a real encoder leaves it
+            mask[i, :len(t)] = True
+        return hidden, mask
+
+    m.encode_text = fake_encode_text
+    batch = ['the sound of rain', 'the sound of playing piano', 'the sound of rain', 'a dog']
+    ctx, msk = m.encode_text_cached(batch)
+    assert calls == [['the sound of rain', 'the sound of playing piano', 'a dog']]
+    joint, jmask = fake_encode_text(batch)
+    assert torch.equal(msk, jmask) and torch.equal(ctx[msk], joint[jmask]) and not ctx[~msk].any()
+    ctx2, msk2 = m.encode_text_cached(['a dog', 'the sound of rain'])
+    assert len(calls) == 2                               # only the joint reference call above was added: both prompts were cached
+    assert ctx2.shape == (2, 4, cfg['dim']) and msk2.sum().item() == 6
+    m.encode_text_cached(['something new'])
+    assert calls[-1] == ['something new']

@@ -520,6 +520,34 @@ class E2TTS(Module):
             hidden = self.text_encoder2(input_ids=ids, attention_mask=am)[0]
         return hidden, (am == 1)
 
+    CONTEXT_CACHE_SIZE = 256
+
+    def encode_text_cached(self, prompt):
+        """T5 context for a batch of prompts, encoding every distinct prompt once and remembering it across calls (SURVEY.md 8f
+        N2: the reference re-encodes the whole batch on every network call, X3:2057, i.e. 2 x steps times per sample()).  The
+        per-prompt rows are the encoder output over the prompt's own tokens; padded positions are zero and masked, exactly what
+        the cross-attention key mask (X3:1131) makes of the reference's padded batch."""
+        cache = self.__dict__.setdefault('_ctx_cache', {})
+        prompt = list(prompt)
+        missing = [p for p in dict.fromkeys(prompt) if p not in cache]
+        if missing:
+            hidden, mask = self.encode_text(missing)
+            for i, p in enumerate(missing):
+                n = int(mask[i].sum())
+                if not bool(mask[i, :n].all()):
+                    raise RuntimeError('encode_text returned a mask that is not a prefix (right padding expected)')
+                cache[p] = hidden[i, :n].detach().to(torch.float32).clone()
+            while len(cache) > self.CONTEXT_CACHE_SIZE:
+                cache.pop(next(iter(cache)))
+        rows = [cache[p] for p in prompt]
+        nc = max(int(r.shape[0]) for r in rows)
+        context = rows[0].new_zeros(len(rows), nc, rows[0].shape[1])
+        context_mask = torch.zeros(len(rows), nc, dtype=torch.bool, device=rows[0].device)
+        for i, r in enumerate(rows):
+            context[i, :r.shape[0]] = r
+            context_mask[i, :r.shape[0]] = True
+        return context, context_mask
+
     VIDEO_FEATURE_SUFFIX = {'clip_vit': '.generated.npz', 'clip_vit2': '.generated.clip_vit2.npz', 'clip_convnext': '.generated.clip_convnext.npz',
                             'dinov2': '.generated.dinov2.npz', 'mixed': '.generated.mixed.npz'}
 
@@ -656,7 +684,7 @@ class E2TTS(Module):
                 for b in range(batch):
                     if video_drop_prompt[b]:
                         prompt[b] = 'the sound of X X'                               # X3:2053-2056
-            context, context_mask = self.encode_text(prompt)
+            context, context_mask = self.encode_text_cached(prompt)
         context = context.to(device=device, dtype=torch.float32).clone()
         if video_drop_prompt is not None:
             for b in range(batch):
