@@ -16,6 +16,7 @@
  *                                   X3:2090-2113, 162-173, 2255
  *   e2b_sample                      the odeint loop of E2TTS.sample                      X3:2221-2256
  *   e2b_melspec                     MelSpec.forward                                      X3:375-417
+ *   e2b_conv1d_cl / e2b_lstm_layer  EncodecWrapper.decode -> transformers EncodecDecoder                          X3:434-437
  *   e2b_stage_clip                  E2TTS.encode_video with a feature cache present: nearest-video-frame resampling of the
  *                                   cached CLIP embeddings to the latent frame rate, zero padding           X3:1802-1826
  */
@@ -95,6 +96,19 @@ int e2b_melspec(const float* wav_dev, int B, int nw, int n_fft, int hop, int n_m
  * [sum F_b, d] fp32; meta_dev [B,4] int64 = {row offset, F_b, count_b, start_sample_b}; duration_dev [B] double (seconds). */
 int e2b_stage_clip(const float* emb_dev, const long long* meta_dev, const double* duration_dev, int B, int l, int d,
                    int sampling_rate, int frame_size, float* out_dev, e2b_stream stream);
+
+/* EnCodec (SEANet) decoder building blocks, fp32, channels-last [B,T,C]; replace the HuggingFace modules behind
+ * EncodecWrapper.decode (X3:434-437): EncodecConv1d / EncodecConvTranspose1d / EncodecResnetBlock -> e2b_conv1d_cl,
+ * EncodecLSTM -> e2b_lstm_layer.  (video-to-audio-and-piano-rp_b200/e2_tts_pytorch/encodec.py strings them together.)
+ *
+ * y[b,t,co] (+)= bias[co] + sum_{k<K, ci<Ci} w[(k*Ci + ci)*Co + co] * act(x[b, t-(K-1)+k, ci]);  rows before the sequence are
+ * zero (flags & 4: reflected, HF _pad1d);  flags & 1: act = ELU, & 2: accumulate into y.  ldy = row stride of y (>= Co). */
+int e2b_conv1d_cl(const float* x_dev, const float* w_dev, const float* bias_dev, float* y_dev, int B, int T, int Ci, int Co, int K,
+                  int ldy, int flags, e2b_stream stream);
+/* One nn.LSTM layer.  gx_dev [B,T,4H] = x W_ih^T + b_ih + b_hh (gates i,f,g,o); whh_packed_dev [H/4][H][4 units][4 gates];
+ * hseq_dev [B,T,H] = h_t (+ skip_dev[b,t,:] when not NULL); hbuf_dev: 2*H*B floats of scratch; counter_dev: one unsigned. */
+int e2b_lstm_layer(const float* gx_dev, const float* whh_packed_dev, const float* skip_dev, float* hseq_dev, float* hbuf_dev,
+                   unsigned* counter_dev, int B, int T, int H, e2b_stream stream);
 
 /* algorithmic FLOPs of one e2b_forward at the prepared shape as executed (skipped null-pass attn2 not counted) */
 double e2b_forward_flops(e2b_handle* h);

@@ -159,7 +159,8 @@ def test_elementwise_kernels_stay_inside_their_outputs(B, N, C_):
     # dwconv
     raw, y, pad = _guarded((B, N, C_))
     wt = (torch.randn(31, C_, device=DEV) / 5).contiguous()
-    kcheck(L().e2b_dwconv_launch(P(x), P(y), P(wt), P(torch.randn(C_, device=DEV)), P(lens), B, N, C_, 31, sp()))
+    cb = torch.randn(C_, device=DEV)
+    kcheck(L().e2b_dwconv_launch(P(x), P(y), P(wt), P(cb), P(lens), B, N, C_, 31, sp()))
     torch.cuda.synchronize()
     assert _guards_intact(raw, pad) and torch.isfinite(y).all()
     # rmsnorm, bf16 and fp32 outputs, with skipped leading rows

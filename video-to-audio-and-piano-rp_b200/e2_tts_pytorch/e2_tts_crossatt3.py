@@ -388,8 +388,9 @@ class MelSpec(Module):
 
 
 class EncodecWrapper(Module):
-    """EnCodec latent encoder / decoder wrapper (reference X3:419-437).  Frozen third-party network, outside the hot path
-    (SURVEY.md section 8f row N1): delegates to HuggingFace `transformers` exactly like the reference."""
+    """EnCodec latent encoder / decoder wrapper (reference X3:419-437).  The weights and the encoder stay HuggingFace
+    `transformers` like in the reference; the decoder (the vocoder downstream of the sampler) runs
+    on libe2b."""
 
     def __init__(self, path):
         super().__init__()
@@ -405,9 +406,22 @@ class EncodecWrapper(Module):
             inputs = self.processor(raw_audio=waveform[0], sampling_rate=self.processor.sampling_rate, return_tensors='pt')
             return self.model.encoder(inputs.input_values)
 
+    def decode_batch(self, emb):
+        """Float[b, 128, t] latents -> Float[b, 1, 320 t] waveforms on libe2b (csrc/encodec.cu)."""
+        if not emb.is_cuda:
+            raise RuntimeError('EncodecWrapper.decode runs on CUDA tensors only: libe2b has no CPU path')
+        dec = self.__dict__.get('_b200')
+        if dec is None or dec.device != emb.device:
+            from .encodec import EncodecDecoderB200
+            cfg = self.model.config
+            dec = EncodecDecoderB200(self.model.decoder.state_dict(), emb.device, upsampling_ratios=tuple(cfg.upsampling_ratios),
+                                     num_lstm_layers=cfg.num_lstm_layers)
+            self.__dict__['_b200'] = dec
+        return dec(emb)
+
     def decode(self, emb):
-        with torch.no_grad():
-            return self.model.decoder(emb)[0]
+        """Reference semantics (X3:434-437): the decoder output of the FIRST batch item, Float[1, samples]."""
+        return self.decode_batch(emb)[0]
 
 
 GUIDANCE_PASSES = {'null': _lib.DROP_CLIP | _lib.DROP_CTX, 'drop_t5': _lib.DROP_CTX, 'drop_clip': _lib.DROP_CLIP,
@@ -725,11 +739,19 @@ class E2TTS(Module):
             assert not exists(self.vocos), '`use_vocos` should not be turned on if you are passing in a custom `vocoder` on sampling'
             out = vocoder(out.transpose(1, 2))
         elif exists(self.vocos):
-            audio = []
-            for mel, one_mask in zip(out, mask):
-                one = mel[one_mask].transpose(0, 1)[None]
-                audio.append(self.vocos.decode(one).reshape(-1))
-            out = audio
+            if hasattr(self.vocos, 'decode_batch') and int(duration.min()) >= 7:
+                # one batched decode instead of the reference's per-clip loop: the decoder is causal (left padding, LSTM), so the
+                # first lens_i * hop samples of a padded sequence equal the decode of its valid prefix -- as long as the clip is
+                # longer than the first conv's reflect padding (6 frames), which looks at the samples after the left edge
+                wav = self.vocos.decode_batch(out.transpose(1, 2))
+                hop = wav.shape[-1] // n
+                out = [wav[i, 0, :int(duration[i]) * hop] for i in range(batch)]
+            else:
+                audio = []
+                for mel, one_mask in zip(out, mask):
+                    one = mel[one_mask].transpose(0, 1)[None]
+                    audio.append(self.vocos.decode(one).reshape(-1))
+                out = audio
         if exists(save_to_filename):                                                 # X3:2289-2303
             import torchaudio
             assert exists(vocoder) or exists(self.vocos)
