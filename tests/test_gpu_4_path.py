@@ -176,3 +176,31 @@ def test_graph_replay_is_bit_identical_to_eager(apg):
     eager1 = run(y1, clip1)                                # first sighting after the signature changed: eager again
     assert torch.equal(via_graph, eager1)
     assert not torch.equal(via_graph, eager)
+
+
+def test_graph_replay_follows_new_lengths_and_context():
+    """Clip lengths, context lengths and pass data live in device buffers that set_conditions rewrites: a replayed graph must use
+    the new ones (nothing length-dependent may be baked into a captured launch)."""
+    g, r, cfg, bt = load_gold('tiny_x3.pt')
+    m, _ = build_model(cfg, r['weight_seed'])
+    d = dev(bt)
+    n = d['y0'].shape[1]
+
+    def run(lens, ctx_mask, steps=r['steps']):
+        return m.sample(torch.zeros_like(d['y0']), text=d['clip'], lens=lens, duration=lens, steps=steps, cfg_strength=r['cfg_strength'],
+                        remove_parallel_component=False, sway_sampling=True, return_raw_output=True, context=d['ctx'], context_mask=ctx_mask,
+                        frames=d['frames'], noise=d['y0'])
+
+    full = torch.full_like(d['lens'], n)
+    run(full, d['ctx_mask'])
+    run(full, d['ctx_mask'])                                  # captured
+    short = torch.clamp(d['lens'] - 3, min=1)
+    short[0] = n                                              # keep the padded length
+    cm = d['ctx_mask'].clone()
+    cm[:, -1] = False
+    cm[:, 0] = True
+    via_graph = run(short, cm)                                # replayed with new lengths / context mask
+    run(short, cm, steps=r['steps'] + 1)                      # other signature: drops back to eager ...
+    eager = run(short, cm)                                    # ... and so does the first call after it
+    mask = eo.lens_to_mask(short.cpu(), n)
+    assert torch.equal(via_graph.cpu()[mask], eager.cpu()[mask])
