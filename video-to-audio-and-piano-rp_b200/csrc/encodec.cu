@@ -19,10 +19,11 @@
 namespace e2b {
 
 constexpr int CV_THREADS = 128;
-constexpr int CV_TPT = 16;          // outputs (time steps) per thread
+constexpr int CV_TPT = 16;          // time steps per thread
+constexpr int CV_NCO = 2;           // output channels per thread (4 x 8 time steps was slower: 16 weight loads per step)
 
 // threads: co_l = tid % COB (output channel inside the tile), tg = tid / COB (time group); a block covers CV_TPT * (128 / COB)
-// time steps of COB output channels.
+// time steps of CV_NCO * COB output channels.
 __global__ void __launch_bounds__(CV_THREADS) conv1d_cl_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                               const float* __restrict__ bias, float* __restrict__ y, int T, int Ci,
                                                               int Co, int K, int ldy, int cob, int flags) {
@@ -47,34 +48,59 @@ __global__ void __launch_bounds__(CV_THREADS) conv1d_cl_kernel(const float* __re
     reinterpret_cast<float4*>(xs)[idx] = v;
   }
   __syncthreads();
+  // Each thread produces CV_TPT time steps of CV_NCO output channels (co, co + cob, ...): the broadcast 16-byte shared-memory
+  // load of four input values then feeds 4 * CV_NCO FMAs -- with one channel per thread the kernel sat at 20 TFLOP/s, bound by
+  // the load/store unit's return path (one LDS.128 per 4 FFMA), not by the FMA pipe.
   const int co_l = threadIdx.x % cob, tg = threadIdx.x / cob;
-  const int co = blockIdx.y * cob + co_l;
+  const int co = blockIdx.y * CV_NCO * cob + co_l;
   if (co >= Co) return;
-  const int tl0 = tg * CV_TPT;                         // first local time step of this thread
-  float acc[CV_TPT];
-  const float bv = bias ? __ldg(bias + co) : 0.f;
-  float* yb = y + ((size_t)b * T + t0 + tl0) * ldy + co;
+  int cc[CV_NCO];
+  bool ok[CV_NCO];
 #pragma unroll
-  for (int t = 0; t < CV_TPT; ++t) acc[t] = ((flags & 2) && t0 + tl0 + t < T) ? yb[(size_t)t * ldy] + bv : bv;
-  for (int k = 0; k < K; ++k) {
-    const float* wk = w + (size_t)k * Ci * Co + co;
-    const float* xk = xs + (size_t)(tl0 + k) * Ci;
-    for (int ci = 0; ci < Ci; ci += 4) {
-      const float w0 = __ldg(wk + (size_t)ci * Co), w1 = __ldg(wk + (size_t)(ci + 1) * Co), w2 = __ldg(wk + (size_t)(ci + 2) * Co),
-                  w3 = __ldg(wk + (size_t)(ci + 3) * Co);
+  for (int c = 0; c < CV_NCO; ++c) {
+    ok[c] = co + c * cob < Co;
+    cc[c] = ok[c] ? co + c * cob : co;                  // channels beyond Co alias the first one and are not stored
+  }
+  const int tl0 = tg * CV_TPT;                          // first local time step of this thread
+  float acc[CV_NCO][CV_TPT];
+  float* yb = y + ((size_t)b * T + t0 + tl0) * ldy;
 #pragma unroll
-      for (int t = 0; t < CV_TPT; ++t) {
-        const float4 xv = *reinterpret_cast<const float4*>(xk + (size_t)t * Ci + ci);
-        acc[t] = fmaf(w0, xv.x, acc[t]);
-        acc[t] = fmaf(w1, xv.y, acc[t]);
-        acc[t] = fmaf(w2, xv.z, acc[t]);
-        acc[t] = fmaf(w3, xv.w, acc[t]);
+  for (int c = 0; c < CV_NCO; ++c) {
+    const float bv = bias ? __ldg(bias + cc[c]) : 0.f;
+#pragma unroll
+    for (int t = 0; t < CV_TPT; ++t) acc[c][t] = ((flags & 2) && t0 + tl0 + t < T) ? yb[(size_t)t * ldy + cc[c]] + bv : bv;
+  }
+  // Taps and input channels flatten into one loop: with channels-last rows the K x Ci window of output t is the contiguous run
+  // xs[(tl0 + t) * Ci + j], j < K * Ci, and the weights are w[j * Co + co].
+  const int KC = K * Ci;
+  const float* x0 = xs + (size_t)tl0 * Ci;
+  for (int j = 0; j < KC; j += 4) {
+    const float* wj = w + (size_t)j * Co;
+    float wv[CV_NCO][4];
+#pragma unroll
+    for (int c = 0; c < CV_NCO; ++c) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wv[c][u] = __ldg(wj + (size_t)u * Co + cc[c]);
+    }
+#pragma unroll
+    for (int t = 0; t < CV_TPT; ++t) {
+      const float4 xv = *reinterpret_cast<const float4*>(x0 + (size_t)t * Ci + j);
+#pragma unroll
+      for (int c = 0; c < CV_NCO; ++c) {
+        acc[c][t] = fmaf(wv[c][0], xv.x, acc[c][t]);
+        acc[c][t] = fmaf(wv[c][1], xv.y, acc[c][t]);
+        acc[c][t] = fmaf(wv[c][2], xv.z, acc[c][t]);
+        acc[c][t] = fmaf(wv[c][3], xv.w, acc[c][t]);
       }
     }
   }
 #pragma unroll
-  for (int t = 0; t < CV_TPT; ++t)
-    if (t0 + tl0 + t < T) yb[(size_t)t * ldy] = acc[t];
+  for (int c = 0; c < CV_NCO; ++c) {
+    if (!ok[c]) continue;
+#pragma unroll
+    for (int t = 0; t < CV_TPT; ++t)
+      if (t0 + tl0 + t < T) yb[(size_t)t * ldy + cc[c]] = acc[c][t];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------- LSTM layer
@@ -161,8 +187,8 @@ extern "C" int e2b_conv1d_cl(const float* x_dev, const float* w_dev, const float
   if (B <= 0 || T <= 0) return 0;
   if (Ci <= 0 || Ci % 4 || Co <= 0 || K <= 0 || ldy < Co) { e2b_set_kernel_error("conv1d_cl: bad shape Ci=%d Co=%d K=%d ldy=%d", Ci, Co, K, ldy); return -1; }
   if (B > 65535) { e2b_set_kernel_error("conv1d_cl: at most 65535 sequences per call"); return -1; }
-  int cob = 8;
-  while (cob < Co && cob < CV_THREADS) cob <<= 1;
+  int cob = 4;                                        // threads along the channel axis; a block covers CV_NCO * cob output channels
+  while (CV_NCO * cob < Co && cob < CV_THREADS) cob <<= 1;
   const int TT = CV_TPT * (CV_THREADS / cob);
   const size_t smem = (size_t)(TT + K - 1) * Ci * sizeof(float);
   if (smem > 200 * 1024) { e2b_set_kernel_error("conv1d_cl: input window of %zu bytes does not fit in shared memory", smem); return -1; }
@@ -175,7 +201,7 @@ extern "C" int e2b_conv1d_cl(const float* x_dev, const float* w_dev, const float
     configured = 200 * 1024;
   }
   ProfScope ps(stream, "conv1d_cl", (long long)B * T, Co, K * Ci, 2.0 * B * T * (double)Co * K * Ci, 4.0 * B * T * ((double)Ci + Co));
-  dim3 grid((T + TT - 1) / TT, (Co + cob - 1) / cob, B);
+  dim3 grid((T + TT - 1) / TT, (Co + CV_NCO * cob - 1) / (CV_NCO * cob), B);
   conv1d_cl_kernel<<<grid, CV_THREADS, smem, stream>>>(x_dev, w_dev, bias_dev, y_dev, T, Ci, Co, K, ldy, cob, flags);
   return check_launch("conv1d_cl");
 }
