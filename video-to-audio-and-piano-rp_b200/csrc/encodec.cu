@@ -12,6 +12,7 @@
 //               unit-major global buffer and a grid barrier per step.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
 
 #include "kernels.h"
 #include "prof.h"
@@ -112,9 +113,13 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(counter, 1u);
-    unsigned v;
+    unsigned v, spins = 0;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (++spins > (1u << 28)) {      // a protocol bug (or a CTA that never became resident) must fail the launch, not hang the GPU
+        printf("e2b: lstm grid barrier timed out (block %d)\n", blockIdx.x);
+        __trap();
+      }
     } while (v < target);
   }
   __syncthreads();
@@ -227,6 +232,9 @@ extern "C" int e2b_lstm_layer(const float* gx_dev, const float* whh_packed_dev, 
   if (cudaMemsetAsync(counter_dev, 0, sizeof(unsigned), stream) != cudaSuccess) { e2b_set_kernel_error("lstm_layer: counter reset failed"); return -1; }
   ProfScope ps(stream, "lstm_layer", (long long)B * T, 4 * H, H, 2.0 * B * T * 4.0 * H * H, 4.0 * B * T * 6.0 * H);
   // every CTA must be resident at once (grid barrier): H / 4 <= SM count and one CTA per SM by its shared-memory footprint
-  lstm_layer_kernel<<<H / LS_UPC, LS_THREADS, smem, stream>>>(gx_dev, whh_packed_dev, skip_dev, hseq_dev, hbuf_dev, counter_dev, B, T, H);
+  // (cooperative launch: the runtime refuses the launch instead of letting the barrier deadlock if the CTAs cannot all be resident)
+  void* kargs[] = {(void*)&gx_dev, (void*)&whh_packed_dev, (void*)&skip_dev, (void*)&hseq_dev, (void*)&hbuf_dev, (void*)&counter_dev, (void*)&B, (void*)&T, (void*)&H};
+  const cudaError_t le = cudaLaunchCooperativeKernel((const void*)lstm_layer_kernel, dim3(H / LS_UPC), dim3(LS_THREADS), kargs, smem, stream);
+  if (le != cudaSuccess) { e2b_set_kernel_error("lstm_layer cooperative launch: %s", cudaGetErrorString(le)); return -1; }
   return check_launch("lstm_layer");
 }
