@@ -88,6 +88,7 @@ def test_batched_decode_of_padded_latents_equals_per_clip_decode():
     hop = full.shape[-1] // 23
     for i, n in enumerate(lens):
         one = dec(emb[i:i + 1, :, :n].contiguous())
-        assert torch.equal(one[0, 0], full[i, 0, :n * hop])
+        # (equal up to summation order: the LSTM kernel splits its dot products differently for different batch sizes)
+        assert rel(one[0, 0], full[i, 0, :n * hop]) < 2e-6
         ref = eo.decode(g['sd'], emb[i:i + 1, :, :n].cpu(), g['cfg'])
         assert rel(one.cpu(), ref) < 1e-5

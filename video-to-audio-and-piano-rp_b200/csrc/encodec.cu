@@ -136,7 +136,12 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_layer_kernel(const float* 
   float* h_s = sm + (size_t)H * LS_UPC * 4;                  // [H][B]
   const int u0 = blockIdx.x * LS_UPC;
   for (int i = threadIdx.x; i < H * LS_UPC; i += LS_THREADS) w_s[i] = __ldg(reinterpret_cast<const float4*>(whh) + (size_t)blockIdx.x * H * LS_UPC + i);
-  const int pairs = B * LS_UPC;                              // (b, u) pairs of this CTA: thread p, p + 256, ...
+  const int pairs = B * LS_UPC;                              // (b, u) pairs of this CTA
+  // Few sequences (a single clip = 16 pairs): the 512-long dot products would run on half a warp.  The H range is then split
+  // into `nslice` slices over otherwise idle threads and the partial gate sums are combined through shared memory.
+  int nslice = 1;
+  while (nslice < 16 && 2 * nslice * pairs <= LS_THREADS && H % (2 * nslice) == 0) nslice <<= 1;
+  float4* red = reinterpret_cast<float4*>(h_s + (size_t)H * B);          // [nslice][pairs] partial (i, f, g, o)
   constexpr int MAXP = 4;                                    // up to 256 batch items per launch
   float c[MAXP];
 #pragma unroll
@@ -148,29 +153,64 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_layer_kernel(const float* 
       for (int i = threadIdx.x; i < H * B / 4; i += LS_THREADS) reinterpret_cast<float4*>(h_s)[i] = __ldcg(reinterpret_cast<const float4*>(hprev) + i);
     }
     __syncthreads();
-#pragma unroll
-    for (int q = 0; q < MAXP; ++q) {
-      const int p = threadIdx.x + q * LS_THREADS;
-      if (p < pairs) {
-        const int u = p / B, b = p - u * B;                  // consecutive lanes = consecutive batch items
+    auto finish = [&](int u, int b, float ai, float af, float ag, float ao, float& cs) {
+      const float ig = 1.f / (1.f + expf(-ai)), fg = 1.f / (1.f + expf(-af)), gg = tanhf(ag), og = 1.f / (1.f + expf(-ao));
+      cs = fg * cs + ig * gg;
+      const float h = og * tanhf(cs);
+      hcur[(size_t)(u0 + u) * B + b] = h;
+      const size_t o = ((size_t)b * T + t) * H + u0 + u;
+      hseq[o] = skip ? h + __ldg(skip + o) : h;
+    };
+    if (nslice > 1) {
+      const int p = threadIdx.x % pairs, sl = threadIdx.x / pairs;
+      const int u = p / B, b = p - u * B;
+      float ai = 0.f, af = 0.f, ag = 0.f, ao = 0.f;
+      if (sl == 0) {
         const float* g = gx + ((size_t)b * T + t) * 4 * H + u0 + u;
-        float ai = __ldg(g), af = __ldg(g + H), ag = __ldg(g + 2 * H), ao = __ldg(g + 3 * H);
+        ai = __ldg(g); af = __ldg(g + H); ag = __ldg(g + 2 * H); ao = __ldg(g + 3 * H);
+      }
+      if (t > 0 && sl < nslice) {
+        const int j1 = (sl + 1) * (H / nslice);
+        for (int j = sl * (H / nslice); j < j1; ++j) {
+          const float hv = h_s[(size_t)j * B + b];
+          const float4 wv = w_s[j * LS_UPC + u];
+          ai = fmaf(wv.x, hv, ai);
+          af = fmaf(wv.y, hv, af);
+          ag = fmaf(wv.z, hv, ag);
+          ao = fmaf(wv.w, hv, ao);
+        }
+        if (sl > 0) red[(size_t)sl * pairs + p] = make_float4(ai, af, ag, ao);
+      }
+      if (t > 0) __syncthreads();
+      if (sl == 0) {
         if (t > 0) {
-          for (int j = 0; j < H; ++j) {
-            const float hv = h_s[(size_t)j * B + b];
-            const float4 wv = w_s[j * LS_UPC + u];
-            ai = fmaf(wv.x, hv, ai);
-            af = fmaf(wv.y, hv, af);
-            ag = fmaf(wv.z, hv, ag);
-            ao = fmaf(wv.w, hv, ao);
+          for (int k = 1; k < nslice; ++k) {
+            const float4 r = red[(size_t)k * pairs + p];
+            ai += r.x; af += r.y; ag += r.z; ao += r.w;
           }
         }
-        const float ig = 1.f / (1.f + expf(-ai)), fg = 1.f / (1.f + expf(-af)), gg = tanhf(ag), og = 1.f / (1.f + expf(-ao));
-        c[q] = fg * c[q] + ig * gg;
-        const float h = og * tanhf(c[q]);
-        hcur[(size_t)(u0 + u) * B + b] = h;
-        const size_t o = ((size_t)b * T + t) * H + u0 + u;
-        hseq[o] = skip ? h + __ldg(skip + o) : h;
+        finish(u, b, ai, af, ag, ao, c[0]);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < MAXP; ++q) {
+        const int p = threadIdx.x + q * LS_THREADS;
+        if (p < pairs) {
+          const int u = p / B, b = p - u * B;                // consecutive lanes = consecutive batch items
+          const float* g = gx + ((size_t)b * T + t) * 4 * H + u0 + u;
+          float ai = __ldg(g), af = __ldg(g + H), ag = __ldg(g + 2 * H), ao = __ldg(g + 3 * H);
+          if (t > 0) {
+            for (int j = 0; j < H; ++j) {
+              const float hv = h_s[(size_t)j * B + b];
+              const float4 wv = w_s[j * LS_UPC + u];
+              ai = fmaf(wv.x, hv, ai);
+              af = fmaf(wv.y, hv, af);
+              ag = fmaf(wv.z, hv, ag);
+              ao = fmaf(wv.w, hv, ao);
+            }
+          }
+          finish(u, b, ai, af, ag, ao, c[q]);
+        }
       }
     }
     if (t + 1 < T) grid_barrier(counter, (unsigned)(t + 1) * gridDim.x);
@@ -219,7 +259,7 @@ extern "C" int e2b_lstm_layer(const float* gx_dev, const float* whh_packed_dev, 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (H % LS_UPC || H / LS_UPC > sms) { e2b_set_kernel_error("lstm_layer: hidden size %d needs H %% 4 == 0 and H / 4 <= %d SMs", H, sms); return -1; }
   if (B % 4 || B > 256) { e2b_set_kernel_error("lstm_layer: batch %d must be a multiple of 4, at most 256 per call", B); return -1; }
-  const size_t smem = ((size_t)H * LS_UPC * 4 + (size_t)H * B) * sizeof(float);
+  const size_t smem = ((size_t)H * LS_UPC * 4 + (size_t)H * B) * sizeof(float) + LS_THREADS * 16 /*partial sums of sliced dot products*/;
   if (smem > 220 * 1024) { e2b_set_kernel_error("lstm_layer: %zu bytes of shared memory needed (reduce the batch per call)", smem); return -1; }
   static bool configured = false;
   if (!configured) {
