@@ -7,6 +7,9 @@ import bench
 from oracle import synth
 from e2_tts_pytorch import _lib
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+if os.environ.get('EW8_MAX_K'):      # experiment knob: largest K that takes the 8-epilogue-warp GEMM configuration
+    import ctypes
+    ctypes.c_int.in_dll(_lib.lib(), 'e2b_gemm_ew8_max_k').value = int(os.environ['EW8_MAX_K'])
 dev = torch.device('cuda', 0)
 model, _ = bench.shipped_model(dev)
 bt = {k: v.to(dev) for k, v in synth.batch(list(range(B)), 750).items()}
@@ -29,5 +32,5 @@ for r in rows:
 print(f'B={B}: one Euler update = {tot:.3f} ms over {sum(r["count"] for r in rows)} launches')
 for k, (ms, n) in sorted(kinds.items(), key=lambda kv: -kv[1][0]):
     print(f'  {k:14s} {ms:7.3f} ms  {100 * ms / tot:5.1f} %  {n:4d} launches  {1e3 * ms / n:7.1f} us each')
-for r in sorted(rows, key=lambda r: -r['ms'])[:12]:
+for r in sorted(rows, key=lambda r: -r['ms'])[:int(os.environ.get('TOP', 12))]:
     print(f"  {r['kind']:12s} m={r['m']:6d} n={r['n']:5d} k={r['k']:5d} x{r['count']:3d} {1e3*r['ms']/r['count']:7.1f} us  {r['flops']*r['count']/(r['ms']*1e-3)/1e12:7.1f} TF/s")
