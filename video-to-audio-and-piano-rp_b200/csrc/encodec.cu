@@ -25,7 +25,7 @@ constexpr int CV_NCO = 2;           // output channels per thread (4 x 8 time st
 
 // threads: co_l = tid % COB (output channel inside the tile), tg = tid / COB (time group); a block covers CV_TPT * (128 / COB)
 // time steps of CV_NCO * COB output channels.
-__global__ void __launch_bounds__(CV_THREADS) conv1d_cl_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(CV_THREADS, 4) conv1d_cl_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                               const float* __restrict__ bias, float* __restrict__ y, int T, int Ci,
                                                               int Co, int K, int ldy, int cob, int flags) {
   extern __shared__ __align__(16) float xs[];          // [(TT + K - 1)][Ci]
