@@ -4,7 +4,7 @@
 //     sim = 50 * tanh(q k^T * 64^-0.5 / 50) ; key-length mask ; softmax (fp32) ; out = attn v ;
 //     out *= sigmoid(head_gate)[token, head]
 //
-// One CTA per (128-query tile, head, batch item).  S = Q K^T lives in TMEM (two 128-column buffers), the softmax
+// One persistent CTA per SM walks work items (128-query tile, head, batch item).  S = Q K^T lives in TMEM (two 128-column buffers), the softmax
 // warps read it with tcgen05.ld, write P (bf16) into shared memory in the UMMA K-major SWIZZLE_128B layout, and
 // O += P V accumulates in TMEM over all key tiles.  Because the soft-clamp bounds every logit to [-50, 50],
 // exp(sim) cannot overflow or underflow in fp32/bf16, so no running maximum and no O rescaling is needed:
