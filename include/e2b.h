@@ -10,6 +10,7 @@
  *   e2b_create / e2b_load_weights   E2TTS.__init__ + load_state_dict            X3:1275-1523, inference_v2a.py:117-124
  *   e2b_prepare / e2b_set_conditions  the step-invariant part of sample():       X3:2162-2216 (masks, frames_embed,
  *                                     proj_frames X3:2069, T5 context K/V of every attn2 X3:1131, CLIP stream X3:2040)
+ *   e2b_set_audio_cond              step_cond / cond_proj_in / final where of the in-painting mode   X3:2029-2035, 2224-2228, 2259-2260
  *   e2b_forward                     transformer_with_pred_head for all guidance passes   X3:1993-2088
  *   e2b_transformer_forward         Transformer.forward                                  X3:941-1143
  *   e2b_guided_euler                cfg_transformer_with_pred_head combine + project + one torchdiffeq Euler update
@@ -17,6 +18,7 @@
  *   e2b_sample                      the odeint loop of E2TTS.sample                      X3:2221-2256
  *   e2b_melspec                     MelSpec.forward                                      X3:375-417
  *   e2b_conv1d_cl / e2b_lstm_layer  EncodecWrapper.decode -> transformers EncodecDecoder                          X3:434-437
+ *   e2b_frame_windows / e2b_roll_expand   E2TTS.encode_frames around the Video2RollNet call                X3:1525-1555
  *   e2b_stage_clip                  E2TTS.encode_video with a feature cache present: nearest-video-frame resampling of the
  *                                   cached CLIP embeddings to the latent frame rate, zero padding           X3:1802-1826
  */
@@ -49,7 +51,7 @@ typedef struct e2b_tensor {
 } e2b_tensor;
 
 /* pass flags: which conditions a guidance pass drops (pass 0 must be 0 = full conditioning) */
-enum { E2B_DROP_CLIP = 1, E2B_DROP_CTX = 2, E2B_DROP_ROLL = 4 };
+enum { E2B_DROP_CLIP = 1, E2B_DROP_CTX = 2, E2B_DROP_ROLL = 4, E2B_DROP_AUDIO = 8 };
 
 int e2b_create(const e2b_config* cfg, e2b_handle** out);
 void e2b_destroy(e2b_handle* h);
@@ -65,6 +67,15 @@ int e2b_prepare(e2b_handle* h, int B, int n, int nc, int P);
  * lens_host[B] valid frames per clip, ctx_lens_host[B] valid context tokens, pass_flags_host[P]. */
 int e2b_set_conditions(e2b_handle* h, const float* clip_dev, const float* roll_dev, const float* ctx_dev,
                        const int* lens_host, const int* ctx_lens_host, const int* pass_flags_host, e2b_stream stream);
+
+/* Audio-conditioned / in-painting mode of sample() (lens < duration; X3:2029-2035 cond_proj_in, 2224-2228 step_cond,
+ * 2259-2260 final select; audiocond_snr None).  cond_dev [B,n,num_channels]: the clip's existing latent; cond_lens_host[B]: frames
+ * that carry it (cond_mask = lens_to_mask(lens)); audio_drop_host[B] (or NULL): clips whose condition is zeroed in every pass
+ * (audio_drop_prompt, X3:2019-2020).  Passes with E2B_DROP_AUDIO see a zero condition (the null pass of the reference's CFG).
+ * The network input of every pass gains cond_proj_in(where(cond_mask, cond, 0)) and the last Euler update of e2b_sample writes
+ * where(cond_mask, cond, y).  Needs "cond_proj_in.weight" among the loaded tensors; call after e2b_set_conditions, which
+ * switches the mode off again (cond_dev = NULL does too). */
+int e2b_set_audio_cond(e2b_handle* h, const float* cond_dev, const int* cond_lens_host, const int* audio_drop_host, e2b_stream stream);
 
 /* pred_dev [P,B,n,num_channels] = velocity of every pass at time t for state x_dev [B,n,num_channels]. */
 int e2b_forward(e2b_handle* h, const float* x_dev, float t, float* pred_dev, e2b_stream stream);
@@ -109,6 +120,17 @@ int e2b_conv1d_cl(const float* x_dev, const float* w_dev, const float* bias_dev,
  * hseq_dev [B,T,H] = h_t (+ skip_dev[b,t,:] when not NULL); hbuf_dev: 2*H*B floats of scratch; counter_dev: one unsigned. */
 int e2b_lstm_layer(const float* gx_dev, const float* whh_packed_dev, const float* skip_dev, float* hseq_dev, float* hbuf_dev,
                    unsigned* counter_dev, int B, int T, int H, e2b_stream stream);
+
+/* Piano-roll front end around Video2RollNet (E2TTS.encode_frames, X3:1525-1555).
+ * e2b_frame_windows: the network input -- for every frame i of x_dev [b, t, frame_elems] its `window` (5) clamped neighbours
+ *   out_dev[(b*t + i), j, :] = x[b, clamp(i + j - window/2, 0, t-1), :]   (replaces the Python double loop at X3:1530-1538).
+ * e2b_roll_expand: logits_dev [b*t, notes] (network output) -> roll_dev [b, l, notes] = sigmoid, every row repeated `repeat` (3)
+ *   times, cut or zero-padded to l frames (X3:1541-1554). */
+int e2b_frame_windows(const float* x_dev, float* out_dev, int b, int t, long long frame_elems, int window, e2b_stream stream);
+int e2b_roll_expand(const float* logits_dev, float* roll_dev, int b, int t, int l, int notes, int repeat, e2b_stream stream);
+
+/* sizeof(e2b_config) as this library was compiled: lets a binding check its own struct definition before e2b_create reads it */
+int e2b_config_size(void);
 
 /* algorithmic FLOPs of one e2b_forward at the prepared shape as executed (skipped null-pass attn2 not counted) */
 double e2b_forward_flops(e2b_handle* h);

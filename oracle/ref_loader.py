@@ -107,7 +107,8 @@ SHIPPED_TRANSFORMER = dict(depth=12, dim=1024, dim_text=1280, heads=16, dim_head
                            if_cross_attn=True, if_audio_conv=True, if_text_conv=True)
 
 
-def build_reference_model(transformer: dict | None = None, seed: int = 0, num_channels: int = 128):
+def build_reference_model(transformer: dict | None = None, seed: int = 0, num_channels: int = 128,
+                          if_cond_proj_in: bool = False):
     """E2TTS as src/inference_v2a.py:74-110 builds it, minus the pretrained encoders (no weights offline)."""
     import torch
     x3 = load_x3()
@@ -118,7 +119,7 @@ def build_reference_model(transformer: dict | None = None, seed: int = 0, num_ch
             transformer=dict(transformer or SHIPPED_TRANSFORMER),
             tokenizer='char_utf8',
             audiocond_drop_prob=1.1, cond_drop_prob=-0.1, prompt_drop_prob=-0.1,
-            if_cond_proj_in=False, if_embed_text=False, if_text_encoder2=False, if_clip_encoder=False,
+            if_cond_proj_in=if_cond_proj_in, if_embed_text=False, if_text_encoder2=False, if_clip_encoder=False,
             num_channels=num_channels, sampling_rate=24000,
         )
     m.vocos = None
@@ -127,12 +128,13 @@ def build_reference_model(transformer: dict | None = None, seed: int = 0, num_ch
 
 
 def reference_sample(m, *, y0, clip, ctx, ctx_mask, frames_embed=None, lens=None, steps=32, cfg_strength=2.0,
-                     remove_parallel_component=False, sway_sampling=True):
+                     remove_parallel_component=False, sway_sampling=True, cond=None, cond_lens=None, audio_drop_prompt=None):
     """Run the reference's own E2TTS.sample on injected conditions.
 
     y0 replaces the torch.randn_like draw at X3:2248 (the only RNG use inside sample()); the CLIP stream enters as
     the float `text=` tensor (X3:2040); T5 output enters by overriding encode_text (X3:2057); a precomputed piano-roll
-    enters by overriding encode_frames (X3:2170).
+    enters by overriding encode_frames (X3:2170).  With `cond` / `cond_lens` the call is the in-painting mode: the
+    reference's `lens` = cond_lens < `duration` = lens (X3:2196-2228, 2259-2260).
     """
     import torch
     b, n, _ = y0.shape
@@ -155,10 +157,11 @@ def reference_sample(m, *, y0, clip, ctx, ctx_mask, frames_embed=None, lens=None
     try:
         with contextlib.redirect_stdout(io.StringIO()):
             out = m.sample(
-                cond=torch.zeros(b, n, y0.shape[-1]), text=clip.clone(), duration=lens.clone(), lens=lens.clone(),
+                cond=torch.zeros(b, n, y0.shape[-1]) if cond is None else cond.clone(), text=clip.clone(), duration=lens.clone(),
+                lens=lens.clone() if cond_lens is None else cond_lens.clone(),
                 steps=steps, cfg_strength=cfg_strength, remove_parallel_component=remove_parallel_component,
                 sway_sampling=sway_sampling, prompt=['the sound of'] * b, video_drop_prompt=[False] * b,
-                audio_drop_prompt=None, frames=frames_arg, return_raw_output=True)
+                audio_drop_prompt=audio_drop_prompt, frames=frames_arg, return_raw_output=True)
     finally:
         torch.randn_like = real_randn_like
     assert len(calls) == 1

@@ -52,6 +52,33 @@ def noise(i: int, n: int, d: int = 128) -> torch.Tensor:
     return torch.randn(n, d, generator=_gen(4000 + i))
 
 
+def audio_condition(i: int, n: int, d: int = 128) -> torch.Tensor:
+    """Latent frames of a clip's existing audio (the in-painting condition, X3:2224-2228)."""
+    return torch.randn(n, d, generator=_gen(6000 + i))
+
+
+def grey_frames(i: int, F: int, w: int = 100, h: int = 900) -> torch.Tensor:
+    """[F, w, h, 1] grey-scale frames as the reference caches them for the piano-roll net (X3:1899-1905)."""
+    return torch.rand(F, w, h, 1, generator=_gen(7000 + i))
+
+
+class StandInRollNet(torch.nn.Module):
+    """Deterministic stand-in for the (third-party, pretrained) Video2RollNet in front-end tests: [N, 5, w, h] -> [N, 51]
+    logits that depend on every one of the 5 frames of a window and on position inside the frame."""
+
+    def __init__(self, seed: int = 0):
+        super().__init__()
+        g = _gen(8000 + seed)
+        self.register_buffer('mix', torch.randn(5 * 4, NOTES, generator=g))
+
+    def forward(self, x):
+        n, _, w, h = x.shape
+        rows = torch.tensor([3 % w, 47 % w, 61 % w, w - 1], device=x.device)
+        cols = torch.tensor([5 % h, 300 % h, 640 % h, h - 1], device=x.device)
+        q = x[:, :, rows, cols]                                                      # [N, 5, 4] probe pixels
+        return (q.reshape(n, 20) - 0.5) @ self.mix.to(x.device) * 2.0
+
+
 def waveform(i: int, nw: int = 240000) -> torch.Tensor:
     return torch.rand(nw, generator=_gen(5000 + i)) - 0.5
 
@@ -103,7 +130,7 @@ def rerandomise_zero_init_(state_dict, seed: int = 1, std: float = 0.02):
 
 def random_state_dict(*, depth=12, dim=1024, dim_text=1280, dim_frames=512, heads=16, dim_head=64, frames_heads=8,
                       ff_mult=4, num_channels=128, max_seq_len=8192, num_registers=32, kernel_size=31, seed=0,
-                      live_conditioning=True):
+                      live_conditioning=True, cond_proj_in=False):
     """State dict of the sampling path (SURVEY.md Appendix C key names) drawn from a seeded CPU generator.
 
     Mirrors the distributions the reference constructor would give (nn.Linear / nn.Conv1d default
@@ -190,6 +217,8 @@ def random_state_dict(*, depth=12, dim=1024, dim_text=1280, dim_frames=512, head
     linear('proj_in', dim, num_channels)
     linear('to_pred', num_channels, dim)
     linear('proj_frames', dim_frames, NOTES)
+    if cond_proj_in:                          # E2TTS(if_cond_proj_in=True): the audio-condition projection, X3:1365 (drawn last:
+        linear('cond_proj_in', dim, num_channels)   # the other tensors do not depend on this switch)
     if live_conditioning:
         rerandomise_zero_init_(sd, seed=seed + 1)
     return sd

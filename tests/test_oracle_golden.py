@@ -71,3 +71,47 @@ def test_k_pass_guidance_reduces_to_cfg():
 def test_flops_closed_form():
     assert abs(eo.flops_forward(750) / 1e9 - 1117.56) < 0.01
     assert abs(eo.flops_forward(2250) / 1e9 - 3680.82) < 0.01
+
+
+def test_inpainting_matches_x3():
+    """Audio-conditioned / in-painting mode: golden produced by the reference's own sample() with lens < duration
+    and E2TTS(if_cond_proj_in=True) (oracle/make_golden.py::inpaint)."""
+    g = torch.load(os.path.join(GOLD, 'tiny_x3_inpaint.pt'), weights_only=False)
+    r = g['recipe']
+    cfg = r['arch']
+    sd = synth.random_state_dict(**cfg, seed=r['weight_seed'], cond_proj_in=True)
+    bt = synth.batch(r['clips'], r['n'], lens=r['lens'], nc_list=r['nc_list'], dim_text=cfg['dim_text'], dim=cfg['dim'],
+                     d=cfg['num_channels'], live_frames=r['live_frames'])
+    cond = torch.stack([synth.audio_condition(i, r['n'], cfg['num_channels']) for i in r['clips']])
+    mask = eo.lens_to_mask(bt['lens'], r['n'])
+    kw = dict(y0=bt['y0'], clip=bt['clip'], frames=bt['frames'], ctx=bt['ctx'], ctx_mask=bt['ctx_mask'], lens=bt['lens'],
+              steps=r['steps'], cfg_strength=r['cfg_strength'], cond=cond, cond_lens=torch.tensor(r['cond_lens']), audio_drop=r['audio_drop'])
+    for apg, key in ((False, 'sample_cfg'), (True, 'sample_apg')):
+        out = eo.sample(sd, **kw, remove_parallel_component=apg)
+        assert rel(out[mask], g[key][mask]) < 1e-5
+        # conditioned frames come back verbatim (X3:2259-2260), the generated ones differ from an unconditioned run
+        cm = eo.lens_to_mask(torch.tensor(r['cond_lens']), r['n'])
+        assert torch.equal(out[cm], cond[cm])
+    plain = eo.sample(sd, **{k: v for k, v in kw.items() if k not in ('cond', 'cond_lens', 'audio_drop')})
+    gen = mask & ~eo.lens_to_mask(torch.tensor(r['cond_lens']), r['n'])
+    assert rel(plain[gen], g['sample_cfg'][gen]) > 1e-3
+
+
+@pytest.mark.parametrize('steps', [32, 64])
+def test_long_trajectory_goldens_are_consistent(steps):
+    """The 32- and 64-point shipped-architecture trajectories (oracle/make_golden.py::shipped_long): recorded grid = the sway
+    grid of the oracle, last recorded state = the returned sample, states are distinct and finite.  (Running the oracle over
+    the whole trajectory takes minutes per clip; the GPU suite compares the CUDA path against these files, and the oracle is
+    pinned to X3 bit for bit at 2-6 updates by the tests above.)"""
+    path = os.path.join(GOLD, f'shipped_x3_s{steps}.pt')
+    if not os.path.exists(path):
+        pytest.skip('fixture not generated')
+    g = torch.load(path, weights_only=False)
+    r = g['recipe']
+    assert r['steps'] == steps and r['n'] == 750 and r['cfg_strength'] == 2.0
+    assert torch.equal(g['grid'], eo.sway_grid(steps))
+    assert g['updates'][-1] == steps - 1 and len(g['updates']) == g['states'].shape[0]
+    assert torch.equal(g['states'][-1], g['sample_cfg'])
+    assert torch.isfinite(g['states']).all()
+    for a, b in zip(g['states'][:-1], g['states'][1:]):
+        assert rel(a, b) > 1e-2

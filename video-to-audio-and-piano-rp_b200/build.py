@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libe2b.so')
-SOURCES = ['gemm.cu', 'attention.cu', 'attention_f32.cu', 'elementwise.cu', 'melspec.cu', 'staging.cu', 'encodec.cu', 'engine.cu', 'prof.cu']
+SOURCES = ['gemm.cu', 'attention.cu', 'attention_f32.cu', 'elementwise.cu', 'melspec.cu', 'staging.cu', 'frames.cu', 'encodec.cu', 'engine.cu', 'prof.cu']
 HEADERS = ['ptx.cuh', 'kernels.h', 'prof.h', os.path.join('..', '..', 'include', 'e2b.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC']
 
@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f'nvcc failed on {s}')
-    cmd = [_nvcc(), '-shared', '-o', LIB, *objs, '-gencode', 'arch=compute_100a,code=sm_100a', '-cudart', 'static']
+    cmd = [_nvcc(), '-shared', '-o', LIB, *objs, '-gencode', 'arch=compute_100a,code=sm_100a', '-cudart', 'static', '-ldl']
     subprocess.check_call(cmd)
     return LIB
 

@@ -526,16 +526,15 @@ extern "C" int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream)
   if (make_tmap_bf16(&a.tmQ, d->q, q_rows, (uint64_t)d->q_col0 + d->heads * 64, d->ldq, ATT_BQ)) return -1;
   if (make_tmap_bf16(&a.tmK, d->k, k_rows, (uint64_t)d->k_col0 + d->heads * 64, d->ldk, ATT_BK)) return -1;
   if (make_tmap_bf16(&a.tmV, d->vt, (uint64_t)kv_batches * d->heads * 64, d->kv_rows_per_batch, d->vt_ld, 64)) return -1;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[E2B_MAX_DEVICES] = {false};
+  bool& conf = configured[e2b_device_slot()];
+  if (!conf) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
     if (e != cudaSuccess) { e2b_set_kernel_error("attention smem attribute: %s", cudaGetErrorString(e)); return -1; }
-    configured = true;
+    conf = true;
   }
   const long long items = (long long)((d->q_rows_per_batch + ATT_BQ - 1) / ATT_BQ) * d->heads * d->batch;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = e2b_num_sms();
   dim3 grid((unsigned)(items < sms ? items : sms));
   ProfScope ps(stream, "attention", (long long)d->batch * d->q_rows_per_batch, d->kv_rows_per_batch, d->heads,
                4.0 * d->batch * d->heads * (double)d->q_rows_per_batch * d->kv_rows_per_batch * 64.0,

@@ -336,7 +336,9 @@ __global__ void __launch_bounds__(256) apg_reduce_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) guided_euler_kernel(float* __restrict__ y, const float* __restrict__ pred, int P, size_t pass_stride,
                                                            size_t per_sample, size_t total4, EulerW gw, float dt, int apg,
                                                            float keep_parallel, const double* __restrict__ scratch,
-                                                           __nv_bfloat16* __restrict__ yb, int n_copies) {
+                                                           __nv_bfloat16* __restrict__ yb, int n_copies,
+                                                           const float* __restrict__ inpaint, const int* __restrict__ inpaint_lens,
+                                                           int row4) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 p0 = reinterpret_cast<const float4*>(pred)[i];
     float v[4] = {p0.x, p0.y, p0.z, p0.w};
@@ -369,6 +371,13 @@ __global__ void __launch_bounds__(256) guided_euler_kernel(float* __restrict__ y
     }
     float4 yy = reinterpret_cast<float4*>(y)[i];
     yy.x += dt * v[0]; yy.y += dt * v[1]; yy.z += dt * v[2]; yy.w += dt * v[3];
+    if (inpaint) {
+      // last update of an in-painting call: out = where(cond_mask, cond, out)  (e2_tts_crossatt3.py:2259-2260)
+      const size_t ps4 = per_sample / 4;
+      const int b = (int)(i / ps4);
+      const int pos = (int)((i - (size_t)b * ps4) / row4);
+      if (pos < __ldg(inpaint_lens + b)) yy = __ldg(reinterpret_cast<const float4*>(inpaint) + i);
+    }
     reinterpret_cast<float4*>(y)[i] = yy;
     if (yb) {
       uint2 u;
@@ -434,13 +443,14 @@ extern "C" int e2b_dwconv_launch(const float* x, float* y, const float* w, const
   const uint32_t box[3] = {DW_C, DW_T + 30, 1};
   if (make_tmap_generic(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, x, dims, strides, box)) return -1;
   const int smem = 2 * (DW_T + 30) * DW_C * 4 + 16;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[E2B_MAX_DEVICES] = {false};
+  bool& conf = configured[e2b_device_slot()];
+  if (!conf) {
     if (cudaFuncSetAttribute(dwconv_tma_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       e2b_set_kernel_error("dwconv: shared memory attribute failed");
       return -1;
     }
-    configured = true;
+    conf = true;
   }
   const int total = batch * ((N + DW_T - 1) / DW_T) * ((C + DW_C - 1) / DW_C);
   const int grid = total < 2 * 148 ? total : 2 * 148;
@@ -532,14 +542,25 @@ extern "C" int e2b_cast_pad_launch(const float* src, int lds, void* dst, int ldd
 
 extern "C" int e2b_guided_euler_launch(float* y, const float* pred, int P, int B, long long per_sample, const float* w, float dt,
                                        int apg, float keep_parallel, double* scratch, void* y_b16, int n_copies, cudaStream_t stream) {
+  return e2b_guided_euler_inpaint_launch(y, pred, P, B, per_sample, w, dt, apg, keep_parallel, scratch, y_b16, n_copies, nullptr, nullptr, 0,
+                                         stream);
+}
+
+extern "C" int e2b_guided_euler_inpaint_launch(float* y, const float* pred, int P, int B, long long per_sample, const float* w, float dt,
+                                               int apg, float keep_parallel, double* scratch, void* y_b16, int n_copies,
+                                               const float* inpaint, const int* inpaint_lens, int row_elems, cudaStream_t stream) {
   if (P < 1 || P > EULER_MAX_P) { e2b_set_kernel_error("guided_euler: P=%d out of range", P); return -1; }
+  if (inpaint && (!inpaint_lens || row_elems <= 0 || row_elems % 4 || per_sample % row_elems)) {
+    e2b_set_kernel_error("guided_euler: in-painting needs lengths and a row size that divides the sample size");
+    return -1;
+  }
   if (per_sample % 4) { e2b_set_kernel_error("guided_euler: per-sample size must be a multiple of 4"); return -1; }
   if (apg && (P != 2 || !scratch)) { e2b_set_kernel_error("guided_euler: APG needs exactly one guidance pass and scratch"); return -1; }
   const size_t pass_stride = (size_t)B * per_sample;
   EulerW gw;
   for (int k = 0; k < EULER_MAX_P; ++k) gw.w[k] = (k < P - 1) ? w[k] : 0.f;
   if (apg) {
-    cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * B, stream);
+    if (cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * B, stream) != cudaSuccess) { e2b_set_kernel_error("guided_euler: memset of the APG scratch failed"); return -1; }
     dim3 g(grid_for(per_sample / 4, 256, 64), B);
     apg_reduce_kernel<<<g, 256, 0, stream>>>(pred, pass_stride, per_sample, scratch);
     if (check_launch("apg_reduce")) return -1;
@@ -547,6 +568,27 @@ extern "C" int e2b_guided_euler_launch(float* y, const float* pred, int P, int B
   const size_t total4 = pass_stride / 4;
   ProfScope ps(stream, "guided_euler", P, B, per_sample, 2.0 * P * pass_stride, 4.0 * pass_stride * (P + 2) + 2.0 * pass_stride * n_copies);
   guided_euler_kernel<<<grid_for(total4, 256), 256, 0, stream>>>(y, pred, P, pass_stride, per_sample, total4, gw, dt, apg,
-                                                                keep_parallel, scratch, reinterpret_cast<__nv_bfloat16*>(y_b16), n_copies);
+                                                                keep_parallel, scratch, reinterpret_cast<__nv_bfloat16*>(y_b16), n_copies,
+                                                                inpaint, inpaint_lens, row_elems / 4);
   return check_launch("guided_euler");
+}
+
+namespace e2b {
+// dst[b, i, :] = i < lens[b] ? src[b, i, :] : 0      (where(cond_mask, cond, 0), e2_tts_crossatt3.py:2228)
+__global__ void __launch_bounds__(256) mask_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, const int* __restrict__ lens,
+                                                        int n, int c4, size_t total4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / c4;
+    const int b = (int)(row / n), pos = (int)(row - (size_t)b * n);
+    reinterpret_cast<float4*>(dst)[i] = pos < __ldg(lens + b) ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+}  // namespace e2b
+
+extern "C" int e2b_mask_rows_launch(const float* src, float* dst, const int* lens_dev, int B, int n, int C, cudaStream_t stream) {
+  if (C % 4) { e2b_set_kernel_error("mask_rows: C must be a multiple of 4"); return -1; }
+  const size_t total4 = (size_t)B * n * (C / 4);
+  if (!total4) return 0;
+  e2b::mask_rows_kernel<<<grid_for(total4, 256), 256, 0, stream>>>(src, dst, lens_dev, n, C / 4, total4);
+  return check_launch("mask_rows");
 }

@@ -237,13 +237,14 @@ extern "C" int e2b_conv1d_cl(const float* x_dev, const float* w_dev, const float
   const int TT = CV_TPT * (CV_THREADS / cob);
   const size_t smem = (size_t)(TT + K - 1) * Ci * sizeof(float);
   if (smem > 200 * 1024) { e2b_set_kernel_error("conv1d_cl: input window of %zu bytes does not fit in shared memory", smem); return -1; }
-  static size_t configured = 0;
-  if (smem > configured) {
+  static bool configured[E2B_MAX_DEVICES] = {false};
+  bool& conf = configured[e2b_device_slot()];
+  if (!conf) {
     if (cudaFuncSetAttribute(conv1d_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
       e2b_set_kernel_error("conv1d_cl: shared memory attribute failed");
       return -1;
     }
-    configured = 200 * 1024;
+    conf = true;
   }
   ProfScope ps(stream, "conv1d_cl", (long long)B * T, Co, K * Ci, 2.0 * B * T * (double)Co * K * Ci, 4.0 * B * T * ((double)Ci + Co));
   dim3 grid((T + TT - 1) / TT, (Co + CV_NCO * cob - 1) / (CV_NCO * cob), B);
@@ -261,13 +262,14 @@ extern "C" int e2b_lstm_layer(const float* gx_dev, const float* whh_packed_dev, 
   if (B % 4 || B > 256) { e2b_set_kernel_error("lstm_layer: batch %d must be a multiple of 4, at most 256 per call", B); return -1; }
   const size_t smem = ((size_t)H * LS_UPC * 4 + (size_t)H * B) * sizeof(float) + LS_THREADS * 16 /*partial sums of sliced dot products*/;
   if (smem > 220 * 1024) { e2b_set_kernel_error("lstm_layer: %zu bytes of shared memory needed (reduce the batch per call)", smem); return -1; }
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[E2B_MAX_DEVICES] = {false};
+  bool& conf = configured[e2b_device_slot()];
+  if (!conf) {
     if (cudaFuncSetAttribute(lstm_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
       e2b_set_kernel_error("lstm_layer: shared memory attribute failed");
       return -1;
     }
-    configured = true;
+    conf = true;
   }
   if (cudaMemsetAsync(counter_dev, 0, sizeof(unsigned), stream) != cudaSuccess) { e2b_set_kernel_error("lstm_layer: counter reset failed"); return -1; }
   ProfScope ps(stream, "lstm_layer", (long long)B * T, 4 * H, H, 2.0 * B * T * 4.0 * H * H, 4.0 * B * T * 6.0 * H);

@@ -57,6 +57,10 @@ struct e2b_handle {
   float *fourier_w = nullptr, *time_w1 = nullptr, *time_b1 = nullptr;
   float *proj_in_b = nullptr, *to_pred_b = nullptr, *pf_b = nullptr;
   bf16 *proj_in_w = nullptr, *to_pred_w = nullptr, *pf_w = nullptr;
+  // audio-conditioned mode (E2TTS(if_cond_proj_in=True), X3:2029-2035): proj_in and cond_proj_in as ONE GEMM over the two
+  // K-concatenated sources (state | condition), weights [proj_in.weight | cond_proj_in.weight], summed biases
+  bf16* proj_in2_w = nullptr;
+  float* proj_in2_b = nullptr;
   float* rope = nullptr;            // [max_pos, 32, 2]
   int rope_rows = 0;
   std::vector<LayerW> L;
@@ -78,8 +82,11 @@ struct e2b_handle {
   float* ystate = nullptr;         // the ODE state the captured graph works on (the caller's y is copied in and out)
   float *hg = nullptr, *fr0 = nullptr, *clip = nullptr, *pred = nullptr, *gam = nullptr, *tcond = nullptr, *times_dev = nullptr;
   double* apg_scratch = nullptr;
-  int *lens_dev = nullptr, *ctx_lens_dev = nullptr;
+  int *lens_dev = nullptr, *ctx_lens_dev = nullptr, *cond_lens_dev = nullptr;
   unsigned char* drop_clip_dev = nullptr;
+  bool audio_cond = false;         // in-painting call: condbf / condm / cond_lens_dev are live
+  bf16* condbf = nullptr;          // [P, B, n, num_channels] bf16 A operand of cond_proj_in: where(cond_mask, cond, 0), 0 for dropped passes
+  float* condm = nullptr;          // [B, n, num_channels] the condition itself, for the final where(cond_mask, cond, out)
   int gam_capacity = 0;
   int pass_flags[8] = {0};
 };
@@ -277,6 +284,7 @@ void free_workspace(e2b_handle* h) {
   h->B = h->n = h->nc = h->P = 0;
   h->gam_capacity = 0;
   h->conditions_set = false;
+  h->audio_cond = false;
 }
 
 // ------------------------------------------------------------------------------------------ gemm descriptor helpers
@@ -398,7 +406,8 @@ int attention_block(e2b_handle* h, int C, int heads, const bf16* w_q, const floa
   return 0;
 }
 
-int side_stream(e2b_handle* h, float* (&s)[2], bf16* sb, int C, int heads, int inner, const Stream3& w, cudaStream_t st) {
+int side_stream(e2b_handle* h, float* (&s)[2], bf16* sb, int C, int heads, int inner, const Stream3& w, cudaStream_t st, const char* name) {
+  e2b::NvtxRange range(name);
   const int HDs = heads * 64;
   CK(e2b_dwconv_launch(s[0], s[1], w.conv_w, w.conv_b, h->lens_dev, h->Bt, h->N, C, h->cfg.kernel_size, st));
   std::swap(s[0], s[1]);
@@ -439,50 +448,59 @@ int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
 
   for (int l = 0; l < c.depth; ++l) {
     const LayerW& w = h->L[l];
-    if (side_stream(h, h->text, h->textb, dt, H, h->inner_t, w.t, st)) return -1;
-    if (side_stream(h, h->frames, h->framesb, df, c.frames_heads, h->inner_f, w.f, st)) return -1;
+    e2b::NvtxRange layer_range("e2b.layer");
+    if (side_stream(h, h->text, h->textb, dt, H, h->inner_t, w.t, st, "e2b.text_stream")) return -1;
+    if (side_stream(h, h->frames, h->framesb, df, c.frames_heads, h->inner_f, w.f, st, "e2b.frames_stream")) return -1;
 
     // cross condition (all three read the pre-update bf16 copies)
     bf16* xnew_b = (l < c.depth / 2) ? h->skipb[l] : h->xtmpb;
     {
-      e2b_gemm_desc d = gdesc(h, M, dim, {{h->xb, dim}, {h->textb, dt}, {h->framesb, df}}, w.tfa_w);
-      d.epi = E2B_EPI_RESID;
-      d.out = h->x[0]; d.ldo = dim; d.resid = h->x[0]; d.ldr = dim;
-      d.out_b16 = xnew_b; d.ldo_b16 = ldb(h, dim); d.split = spl(h, dim);
-      CK(e2b_gemm_launch(&d, st));
-    }
-    if (w.at_w) {
-      e2b_gemm_desc d = gdesc(h, M, dt, {{h->xb, dim}, {h->textb, dt}}, w.at_w);
-      d.epi = E2B_EPI_RESID;
-      d.out = h->text[0]; d.ldo = dt; d.resid = h->text[0]; d.ldr = dt;
-      CK(e2b_gemm_launch(&d, st));
-      e2b_gemm_desc e = gdesc(h, M, df, {{h->xb, dim}, {h->framesb, df}}, w.af_w);
-      e.epi = E2B_EPI_RESID;
-      e.out = h->frames[0]; e.ldo = df; e.resid = h->frames[0]; e.ldr = df;
-      CK(e2b_gemm_launch(&e, st));
+      e2b::NvtxRange r("e2b.cross_condition");
+      {
+        e2b_gemm_desc d = gdesc(h, M, dim, {{h->xb, dim}, {h->textb, dt}, {h->framesb, df}}, w.tfa_w);
+        d.epi = E2B_EPI_RESID;
+        d.out = h->x[0]; d.ldo = dim; d.resid = h->x[0]; d.ldr = dim;
+        d.out_b16 = xnew_b; d.ldo_b16 = ldb(h, dim); d.split = spl(h, dim);
+        CK(e2b_gemm_launch(&d, st));
+      }
+      if (w.at_w) {
+        e2b_gemm_desc d = gdesc(h, M, dt, {{h->xb, dim}, {h->textb, dt}}, w.at_w);
+        d.epi = E2B_EPI_RESID;
+        d.out = h->text[0]; d.ldo = dt; d.resid = h->text[0]; d.ldr = dt;
+        CK(e2b_gemm_launch(&d, st));
+        e2b_gemm_desc e = gdesc(h, M, df, {{h->xb, dim}, {h->framesb, df}}, w.af_w);
+        e.epi = E2B_EPI_RESID;
+        e.out = h->frames[0]; e.ldo = df; e.resid = h->frames[0]; e.ldr = df;
+        CK(e2b_gemm_launch(&e, st));
+      }
     }
     // U-Net skip
     if (l >= c.depth / 2) {
+      e2b::NvtxRange r("e2b.unet_skip");
       e2b_gemm_desc d = gdesc(h, M, dim, {{h->xtmpb, dim}, {h->skipb[c.depth - 1 - l], dim}}, w.skip_w);
       d.epi = E2B_EPI_F32;
       d.out = h->x[0]; d.ldo = dim;
       CK(e2b_gemm_launch(&d, st));
     }
     // audio stream
-    CK(e2b_dwconv_launch(h->x[0], h->x[1], w.conv_w, w.conv_b, h->lens_dev, h->Bt, h->N, dim, c.kernel_size, st));
-    std::swap(h->x[0], h->x[1]);
-    if (norm(h, h->x[0], dim, h->nb, G(l, 0), gam.bstride, h->Bt, 0, st)) return -1;
-    if (attention_block(h, dim, H, w.qkv_w, w.hg_b, h->Bt, -1, st)) return -1;
     {
-      e2b_gemm_desc d = gdesc(h, M, dim, {{h->ob, HD}}, w.out_w);
-      d.epi = E2B_EPI_RESID;
-      d.out = h->x[0]; d.ldo = dim; d.resid = h->x[0]; d.ldr = dim;
-      d.gate = G(l, 1); d.gate_bstride = gam.bstride;
-      d.lens = h->lens_dev; d.rows_per_batch = h->N;
-      CK(e2b_gemm_launch(&d, st));
+      e2b::NvtxRange r("e2b.audio.self_attn");
+      CK(e2b_dwconv_launch(h->x[0], h->x[1], w.conv_w, w.conv_b, h->lens_dev, h->Bt, h->N, dim, c.kernel_size, st));
+      std::swap(h->x[0], h->x[1]);
+      if (norm(h, h->x[0], dim, h->nb, G(l, 0), gam.bstride, h->Bt, 0, st)) return -1;
+      if (attention_block(h, dim, H, w.qkv_w, w.hg_b, h->Bt, -1, st)) return -1;
+      {
+        e2b_gemm_desc d = gdesc(h, M, dim, {{h->ob, HD}}, w.out_w);
+        d.epi = E2B_EPI_RESID;
+        d.out = h->x[0]; d.ldo = dim; d.resid = h->x[0]; d.ldr = dim;
+        d.gate = G(l, 1); d.gate_bstride = gam.bstride;
+        d.lens = h->lens_dev; d.rows_per_batch = h->N;
+        CK(e2b_gemm_launch(&d, st));
+      }
     }
     // cross attention to the T5 context: only for passes whose context is live (a zero context gives exactly 0)
     if (Mc > 0) {
+      e2b::NvtxRange r("e2b.audio.cross_attn");
       if (norm(h, h->x[0], dim, h->nb, G(l, 2), gam.bstride, ctx_batch, 0, st)) return -1;
       if (attention_block(h, dim, H, w.q2_w, w.hg2_b, ctx_batch, l, st)) return -1;
       e2b_gemm_desc o = gdesc(h, Mc, dim, {{h->ob, HD}}, w.out2_w);
@@ -492,6 +510,7 @@ int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
       o.lens = h->lens_dev; o.rows_per_batch = h->N;
       CK(e2b_gemm_launch(&o, st));
     }
+    e2b::NvtxRange ff_range("e2b.audio.ff");
     if (norm(h, h->x[0], dim, h->nb, G(l, 4), gam.bstride, h->Bt, 0, st)) return -1;
     {
       e2b_gemm_desc d = gdesc(h, M, 2 * h->inner, {{h->nb, dim}}, w.ff1_w);
@@ -516,8 +535,9 @@ int init_streams_from_state(e2b_handle* h, cudaStream_t st) {
   const int R = c.num_registers;
   CK(e2b_init_stream_split_launch(h->x[0], h->xb, ldb(h, c.dim), spl(h, c.dim), h->registers, nullptr, -1, nullptr, nullptr, h->Bt, h->n, R,
                                   c.dim, st));
-  e2b_gemm_desc d = gdesc(h, (size_t)h->Bt * h->n, c.dim, {{h->ybf, c.num_channels}}, h->proj_in_w);
-  d.epi = E2B_EPI_F32; d.bias = h->proj_in_b;
+  e2b_gemm_desc d = h->audio_cond ? gdesc(h, (size_t)h->Bt * h->n, c.dim, {{h->ybf, c.num_channels}, {h->condbf, c.num_channels}}, h->proj_in2_w)
+                                  : gdesc(h, (size_t)h->Bt * h->n, c.dim, {{h->ybf, c.num_channels}}, h->proj_in_w);
+  d.epi = E2B_EPI_F32; d.bias = h->audio_cond ? h->proj_in2_b : h->proj_in_b;
   d.out = h->x[0]; d.ldo = c.dim; d.out_b16 = h->xb; d.ldo_b16 = ldb(h, c.dim); d.split = spl(h, c.dim);
   d.rpb_in = h->n; d.rpb_out = h->N; d.row_off = R;
   d.add_table = h->abs_pos; d.ld_add = c.dim;
@@ -625,6 +645,7 @@ extern "C" void e2b_destroy(e2b_handle* h) {
 }
 
 extern "C" long long e2b_launch_count(e2b_handle* h) { return h ? h->launches : 0; }
+extern "C" int e2b_config_size(void) { return (int)sizeof(e2b_config); }
 
 extern "C" int e2b_load_weights(e2b_handle* h, const e2b_tensor* tensors, int n, e2b_stream stream) {
   if (!h) return fail(h, "null handle");
@@ -648,6 +669,26 @@ extern "C" int e2b_load_weights(e2b_handle* h, const e2b_tensor* tensors, int n,
   if (copy_f32(h, w, T + "time_cond_mlp.1.bias", &h->time_b1, dim, -1, st)) return -1;
   if (pack_linear(h, w, "proj_in.weight", &h->proj_in_w, dim, c.num_channels, st)) return -1;
   if (copy_f32(h, w, "proj_in.bias", &h->proj_in_b, dim, -1, st)) return -1;
+  h->proj_in2_w = nullptr; h->proj_in2_b = nullptr;
+  if (w.get("cond_proj_in.weight")) {
+    const e2b_tensor *tp, *tc, *tb;
+    const int nch = c.num_channels;
+    if (need(h, w, "proj_in.weight", &tp, dim, nch) || need(h, w, "cond_proj_in.weight", &tc, dim, nch) || need(h, w, "proj_in.bias", &tb, dim)) return -1;
+    const int ldd = 2 * kx(h, nch);
+    DA(h->wallocs, h->proj_in2_w, (size_t)dim * ldd);
+    int col = 0;
+    if (cast_block(h, tp->dev, nch, 0, 0, nch, nch, h->proj_in2_w, ldd, 0, col, dim, st, &col)) return -1;
+    if (cast_block(h, tc->dev, nch, 0, 0, nch, nch, h->proj_in2_w, ldd, 0, col, dim, st, &col)) return -1;
+    std::vector<float> b0(dim), b1(dim, 0.f);
+    CU(cudaMemcpy(b0.data(), tb->dev, dim * sizeof(float), cudaMemcpyDeviceToHost));
+    if (const e2b_tensor* tcb = w.get("cond_proj_in.bias")) {          // E2TTS(cond_proj_in_bias=False) has none
+      if (need(h, w, "cond_proj_in.bias", &tcb, dim)) return -1;
+      CU(cudaMemcpy(b1.data(), tcb->dev, dim * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    for (int i = 0; i < dim; ++i) b0[i] += b1[i];
+    DA(h->wallocs, h->proj_in2_b, dim);
+    CU(cudaMemcpy(h->proj_in2_b, b0.data(), dim * sizeof(float), cudaMemcpyHostToDevice));
+  }
   if (pack_linear(h, w, "to_pred.weight", &h->to_pred_w, c.num_channels, dim, st)) return -1;
   if (copy_f32(h, w, "to_pred.bias", &h->to_pred_b, c.num_channels, -1, st)) return -1;
   if (pack_linear(h, w, "proj_frames.weight", &h->pf_w, df, c.notes, st, {{c.notes, 64}})) return -1;   // K padded 51 -> 64 with zeros
@@ -720,18 +761,33 @@ extern "C" int e2b_load_weights(e2b_handle* h, const e2b_tensor* tensors, int n,
   return 0;
 }
 
+static int allocate_workspace(e2b_handle* h, int B, int n, int nc, int P);
+
 extern "C" int e2b_prepare(e2b_handle* h, int B, int n, int nc, int P) {
   if (!h) return fail(h, "null handle");
   const e2b_config& c = h->cfg;
   if (B <= 0 || n <= 0 || nc <= 0 || P < 1 || P > 8) return fail(h, "e2b_prepare: bad shape B=%d n=%d nc=%d P=%d", B, n, nc, P);
   if (n > c.max_seq_len) return fail(h, "e2b_prepare: n=%d exceeds max_seq_len=%d", n, c.max_seq_len);   // X3:958
+  if (nc > n + c.num_registers) return fail(h, "e2b_prepare: nc=%d exceeds sequence length %d", nc, n + c.num_registers);
   if (B == h->B && n == h->n && nc == h->nc && P == h->P) return 0;
   drop_graph(h);
   free_workspace(h);
-  h->B = B; h->n = n; h->nc = nc; h->P = P; h->Pctx = P;
+  // The shape is recorded only once every buffer exists: a failed allocation leaves the handle unprepared (B = 0), so a
+  // retry with the same shape allocates again instead of taking the early-out above with null / partial buffers.
+  if (allocate_workspace(h, B, n, nc, P)) {
+    const std::string msg = h->err;
+    free_workspace(h);
+    h->err = msg;
+    return -1;
+  }
+  return 0;
+}
+
+static int allocate_workspace(e2b_handle* h, int B, int n, int nc, int P) {
+  const e2b_config& c = h->cfg;
+  h->n = n; h->nc = nc; h->P = P; h->Pctx = P;
   h->N = n + c.num_registers; h->Bt = B * P; h->M = (size_t)h->Bt * h->N;
   h->Npad = rup(h->N, 8); h->ncpad = rup(nc, 8);
-  if (nc > h->N) return fail(h, "e2b_prepare: nc=%d exceeds sequence length %d", nc, h->N);
   const size_t M = h->M;
   const int dim = c.dim, dt = c.dim_text, df = c.dim_frames;
   const int Cmax = std::max(dim, std::max(dt, df));
@@ -788,6 +844,10 @@ extern "C" int e2b_prepare(e2b_handle* h, int B, int n, int nc, int P) {
   DA(h->sallocs, h->lens_dev, h->Bt);
   DA(h->sallocs, h->ctx_lens_dev, B);
   DA(h->sallocs, h->drop_clip_dev, h->Bt);
+  DA(h->sallocs, h->cond_lens_dev, B);
+  DA(h->sallocs, h->condbf, (size_t)h->Bt * n * c.num_channels * w2);
+  DA(h->sallocs, h->condm, (size_t)B * n * c.num_channels);
+  h->B = B;                        // last: marks the workspace as complete
   return 0;
 }
 
@@ -805,7 +865,7 @@ extern "C" int e2b_set_conditions(e2b_handle* h, const float* clip_dev, const fl
   bool seen_dropped = false;
   std::vector<unsigned char> dc(h->Bt);
   for (int p = 0; p < h->P; ++p) {
-    const int fl = pass_flags_host ? pass_flags_host[p] : (p == 0 ? 0 : (E2B_DROP_CLIP | E2B_DROP_CTX));
+    const int fl = pass_flags_host ? pass_flags_host[p] : (p == 0 ? 0 : (E2B_DROP_CLIP | E2B_DROP_CTX | E2B_DROP_AUDIO));
     if (p == 0 && fl != 0) return fail(h, "pass 0 must keep every condition");
     if (fl & E2B_DROP_CTX) seen_dropped = true;
     else {
@@ -839,6 +899,42 @@ extern "C" int e2b_set_conditions(e2b_handle* h, const float* clip_dev, const fl
   }
   if (set_ctx(h, ctx_dev, ctx_lens_host, st)) return -1;
   h->conditions_set = true;
+  h->audio_cond = false;           // in-painting is per call: e2b_set_audio_cond after this switches it on
+  return 0;
+}
+
+extern "C" int e2b_set_audio_cond(e2b_handle* h, const float* cond_dev, const int* cond_lens_host, const int* audio_drop_host, e2b_stream stream) {
+  if (!h) return fail(h, "null handle");
+  if (!h->conditions_set) return fail(h, "e2b_set_audio_cond: call e2b_set_conditions first");
+  if (!cond_dev) { h->audio_cond = false; return 0; }
+  if (!h->proj_in2_w) return fail(h, "e2b_set_audio_cond: the loaded weights have no cond_proj_in (E2TTS(if_cond_proj_in=False))");
+  if (!cond_lens_host) return fail(h, "e2b_set_audio_cond: cond_lens is required");
+  cudaStream_t st = (cudaStream_t)stream;
+  const e2b_config& c = h->cfg;
+  const size_t per_pass = (size_t)h->B * h->n;
+  std::vector<int> cl(h->B), eff(h->B);
+  for (int b = 0; b < h->B; ++b) {
+    if (cond_lens_host[b] < 0 || cond_lens_host[b] > h->n) return fail(h, "cond_lens[%d]=%d outside [0,%d]", b, cond_lens_host[b], h->n);
+    cl[b] = cond_lens_host[b];
+    eff[b] = (audio_drop_host && audio_drop_host[b]) ? 0 : cl[b];      // audio_drop_prompt zeroes the clip's condition (X3:2019-2020)
+  }
+  // network input: where(cond_mask, cond, 0) with dropped clips zeroed, through h->pred as fp32 scratch -> bf16 per pass
+  CU(cudaMemcpyAsync(h->cond_lens_dev, eff.data(), h->B * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(e2b_mask_rows_launch(cond_dev, h->pred, h->cond_lens_dev, h->B, h->n, c.num_channels, st));
+  for (int p = 0; p < h->P; ++p) {
+    bf16* dst = h->condbf + p * per_pass * ldb(h, c.num_channels);
+    if (h->pass_flags[p] & E2B_DROP_AUDIO) {
+      CU(cudaMemsetAsync(dst, 0, per_pass * ldb(h, c.num_channels) * sizeof(bf16), st));
+    } else if (cast_act(h, h->pred, c.num_channels, dst, c.num_channels, c.num_channels, per_pass, st)) {
+      return -1;
+    }
+  }
+  CU(cudaStreamSynchronize(st));   // eff (host vector) must outlive the async copy; cond_lens_dev is rewritten below
+  // output select: the condition itself below cond_lens (dropped clips included: the reference selects from the caller's cond)
+  CU(cudaMemcpyAsync(h->cond_lens_dev, cl.data(), h->B * sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h->condm, cond_dev, per_pass * c.num_channels * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  h->audio_cond = true;
   return 0;
 }
 
@@ -866,14 +962,17 @@ static int run_sample_steps(e2b_handle* h, float* y_dev, const float* t_grid_hos
   for (int p = 0; p < h->P; ++p)
     if (cast_act(h, y_dev, c.num_channels, h->ybf + p * per_pass * ldb(h, c.num_channels), c.num_channels, c.num_channels, per_pass, st)) return -1;
   for (int s = 0; s < steps - 1; ++s) {
+    e2b::NvtxRange range("e2b.euler_update");
     const float dt = t_grid_host[s + 1] - t_grid_host[s];
     if (init_streams_from_state(h, st)) return -1;
     if (forward_core(h, GamRef{h->gam + (size_t)s * h->nmat * c.dim, 0}, st)) return -1;
     if (pred_head(h, h->pred, st)) return -1;
     // bf16 mode: the Euler kernel also emits the bf16 copies of y that feed the next proj_in; the error-compensated mode
     // needs (hi, lo) pairs, produced by a separate split cast
-    CK(e2b_guided_euler_launch(y_dev, h->pred, h->P, h->B, per_sample, guidance_w_host, dt, apg, keep_parallel, h->apg_scratch,
-                               h->f32 ? nullptr : h->ybf, h->f32 ? 0 : h->P, st));
+    const bool select = h->audio_cond && s == steps - 2;      // out = where(cond_mask, cond, out) folded into the last update
+    CK(e2b_guided_euler_inpaint_launch(y_dev, h->pred, h->P, h->B, per_sample, guidance_w_host, dt, apg, keep_parallel, h->apg_scratch,
+                                       h->f32 ? nullptr : h->ybf, h->f32 ? 0 : h->P, select ? h->condm : nullptr,
+                                       select ? h->cond_lens_dev : nullptr, select ? c.num_channels : 0, st));
     if (h->f32 && s + 1 < steps - 1)
       for (int p = 0; p < h->P; ++p)
         if (cast_act(h, y_dev, c.num_channels, h->ybf + p * per_pass * ldb(h, c.num_channels), c.num_channels, c.num_channels, per_pass, st)) return -1;
@@ -906,6 +1005,7 @@ extern "C" int e2b_sample(e2b_handle* h, float* y_dev, const float* t_grid_host,
   auto put = [&](const void* p, size_t n) { key.insert(key.end(), (const unsigned char*)p, (const unsigned char*)p + n); };
   put(&steps, sizeof steps); put(&apg, sizeof apg); put(&keep_parallel, sizeof keep_parallel);
   put(&h->epoch, sizeof h->epoch); put(&h->P, sizeof h->P); put(h->pass_flags, sizeof(int) * h->P);
+  put(&h->audio_cond, sizeof h->audio_cond);
   put(t_grid_host, sizeof(float) * steps);
   if (h->P > 1) put(guidance_w_host, sizeof(float) * (h->P - 1));
 

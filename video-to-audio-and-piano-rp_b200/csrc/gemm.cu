@@ -554,25 +554,17 @@ int make_tmap_generic(CUtensorMap* m, CUtensorMapDataType dt, int rank, const vo
   return 0;
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+static int num_sms() { return e2b_num_sms(); }
 
 template <int BN, int EPI, int EW>
 static int launch_t(const GemmArgs& a, cudaStream_t st) {
   using Cfg = GemmCfg<BN, EW>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[E2B_MAX_DEVICES] = {false};
+  bool& conf = configured[e2b_device_slot()];
+  if (!conf) {
     cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { e2b_set_kernel_error("gemm smem attribute: %s", cudaGetErrorString(e)); return -1; }
-    configured = true;
+    conf = true;
   }
   const int tiles = ((a.d.M + BM - 1) / BM) * ((a.d.N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -623,9 +615,7 @@ extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
   if (bn256 && d->epi != E2B_EPI_GEGLU) {
     // Few rows (one clip per call): when even the 128x128 tiling fits in one wave, the 128x256 tiling leaves most SMs idle
     // (single 10 s clip: 52 tiles for 148 SMs at N = 1024) -- take the narrower tile (sample() latency 190 -> 166 ms).
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = e2b_num_sms();
     const long long mt = (d->M + BM - 1) / BM;
     if (mt * ((d->N + 127) / 128) <= sms) bn256 = false;
   }

@@ -146,6 +146,14 @@ int e2b_guided_euler_launch(float* y, const float* pred, int P, int B, long long
                             int apg, float keep_parallel, double* scratch, void* y_b16, int n_copies,
                             cudaStream_t stream);
 
+// the same with the final in-painting select folded in: rows below inpaint_lens[b] of sample b take inpaint[b, row, :]
+// (row_elems values per row) instead of the updated state
+int e2b_guided_euler_inpaint_launch(float* y, const float* pred, int P, int B, long long per_sample, const float* w, float dt,
+                                    int apg, float keep_parallel, double* scratch, void* y_b16, int n_copies,
+                                    const float* inpaint, const int* inpaint_lens, int row_elems, cudaStream_t stream);
+// dst[b, i, :] = i < lens_dev[b] ? src[b, i, :] : 0
+int e2b_mask_rows_launch(const float* src, float* dst, const int* lens_dev, int B, int n, int C, cudaStream_t stream);
+
 // mel front end: wav [B, nw] fp32 -> log-mel [B, n_mels, T], T = nw / hop + 1 (center, reflect pad)
 int e2b_melspec_launch(const float* wav, int B, int nw, int n_fft, int hop, int n_mels, const float* window,
                        const float* fb /*[n_fft/2+1, n_mels]*/, const float* twiddle /*[n_fft/2][2]*/, float* out,
@@ -155,5 +163,24 @@ const char* e2b_kernel_last_error(void);
 void e2b_set_kernel_error(const char* fmt, ...);
 
 #ifdef __cplusplus
+}
+
+// Function attributes (dynamic shared-memory opt-in) and the SM count belong to a DEVICE, not to the process: one slot per
+// device ordinal, so a second GPU driven from the same process is configured too.
+constexpr int E2B_MAX_DEVICES = 64;
+inline int e2b_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < E2B_MAX_DEVICES) ? dev : 0;
+}
+inline int e2b_num_sms() {
+  static int sms[E2B_MAX_DEVICES] = {0};
+  const int dev = e2b_device_slot();
+  if (!sms[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = n > 0 ? n : 148;
+  }
+  return sms[dev];
 }
 #endif

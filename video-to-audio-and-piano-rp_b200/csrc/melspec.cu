@@ -116,7 +116,8 @@ extern "C" int e2b_melspec_launch(const float* wav, int B, int nw, int n_fft, in
   if (n_mels <= 0 || B <= 0 || hop <= 0) { e2b_set_kernel_error("melspec: bad arguments"); return -1; }
   const int T = nw / hop + 1;
   const size_t smem = (2 * n_fft + n_fft / 2 + 1 + n_mels * MEL_FR + MEL_THREADS) * sizeof(float);
-  static size_t configured = 0;
+  static size_t configured_bytes[E2B_MAX_DEVICES] = {0};
+  size_t& configured = configured_bytes[e2b_device_slot()];
   if (smem > 48 * 1024 && smem > configured) {
     if (cudaFuncSetAttribute(melspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       e2b_set_kernel_error("melspec: shared memory request %zu failed", smem);

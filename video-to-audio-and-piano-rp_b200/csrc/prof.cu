@@ -19,6 +19,7 @@ std::vector<Rec> g_recs;
 }  // namespace
 
 ProfScope::ProfScope(cudaStream_t s, const char* kind, long long m, long long n, long long k, double flops, double bytes) : idx(-1), st(s) {
+  nvtxRangePushA(kind);
   if (!g_on) return;
   Rec r;
   r.kind = kind; r.m = m; r.n = n; r.k = k; r.flops = flops; r.bytes = bytes;
@@ -30,6 +31,7 @@ ProfScope::ProfScope(cudaStream_t s, const char* kind, long long m, long long n,
 }
 ProfScope::~ProfScope() {
   if (idx >= 0) cudaEventRecord(g_recs[idx].b, st);
+  nvtxRangePop();
 }
 }  // namespace e2b
 

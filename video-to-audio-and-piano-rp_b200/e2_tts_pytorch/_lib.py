@@ -9,7 +9,7 @@ import torch
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG, 'libe2b.so')
 
-DROP_CLIP, DROP_CTX, DROP_ROLL = 1, 2, 4
+DROP_CLIP, DROP_CTX, DROP_ROLL, DROP_AUDIO = 1, 2, 4, 8
 
 
 class Config(C.Structure):
@@ -77,6 +77,7 @@ _SIGS = {
     'e2b_prepare': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     'e2b_set_conditions': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                      C.POINTER(C.c_int), C.c_void_p]),
+    'e2b_set_audio_cond': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
     'e2b_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     'e2b_sample': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.c_int, C.c_float,
                              C.c_void_p]),
@@ -86,6 +87,9 @@ _SIGS = {
                                    C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     'e2b_melspec': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p]),
+    'e2b_frame_windows': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
+    'e2b_roll_expand': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'e2b_config_size': (C.c_int, []),
     'e2b_forward_flops': (C.c_double, [C.c_void_p]),
     'e2b_launch_count': (C.c_longlong, [C.c_void_p]),
     # kernel-level entry points (csrc/kernels.h) used by the unit tests
@@ -130,6 +134,9 @@ def lib():
         for name, (res, args) in _SIGS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
+        if L.e2b_config_size() != C.sizeof(Config):
+            raise RuntimeError(f'{LIB_PATH}: e2b_config is {L.e2b_config_size()} bytes in the library, {C.sizeof(Config)} in this binding '
+                               '(stale build? run build.py --force)')
         _lib = L
     return _lib
 

@@ -175,6 +175,13 @@ class _Engine:
                 self.handle, _lib.ptr(clip), _lib.ptr(roll), _lib.ptr(ctx), _lib.int_array(lens), _lib.int_array(ctx_lens),
                 _lib.int_array(pass_flags), _lib.stream_ptr(self.device)), 'e2b_set_conditions')
 
+    def set_audio_cond(self, cond, cond_lens, audio_drop):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.e2b_set_audio_cond(
+                self.handle, _lib.ptr(cond), _lib.int_array(cond_lens) if cond is not None else None,
+                _lib.int_array([1 if v else 0 for v in audio_drop]) if audio_drop is not None else None,
+                _lib.stream_ptr(self.device)), 'e2b_set_audio_cond')
+
     def forward(self, x, t, P):
         B, n, d = x.shape
         pred = torch.empty(P, B, n, d, device=x.device, dtype=torch.float32)
@@ -302,8 +309,10 @@ class Transformer(Module):
         return super().load_state_dict(*a, **k)
 
     def _standalone_engine(self):
-        if self._engine is not None and getattr(self, '_engine_precision', None) != self.precision:
-            self._engine = None
+        fp = (self.precision, _weights_fingerprint(self))
+        if self._engine is not None and self.__dict__.get('_engine_fp') != fp:
+            self._engine = None                      # precision switch or weights edited since they were packed
+        self.__dict__['_engine_fp'] = fp
         if self._engine is None:
             dev = self.registers.device
             tensors = _named_tensors(self, 'transformer.')
@@ -322,6 +331,11 @@ class Transformer(Module):
         assert n <= self.max_seq_len, f'{n} exceeds the set `max_seq_len` ({self.max_seq_len}) on Transformer'  # X3:958
         if text_embed is None or frames_embed is None or context is None:
             raise NotImplementedError('the CUDA path needs text_embed, frames_embed and context (the shipped call always passes them)')
+        if x.shape[-1] != self.dim or tuple(text_embed.shape) != (b, n, self.dim_text) or tuple(frames_embed.shape) != (b, n, self.dim_frames) \
+                or context.ndim != 3 or context.shape[0] != b or context.shape[-1] != self.dim:
+            raise ValueError(f'Transformer.forward: x {tuple(x.shape)}, text_embed {tuple(text_embed.shape)}, frames_embed '
+                             f'{tuple(frames_embed.shape)}, context {tuple(context.shape)} do not fit dim {self.dim} / dim_text '
+                             f'{self.dim_text} / dim_frames {self.dim_frames}')
         eng = self._standalone_engine()
         if times.ndim == 0:
             times = times.expand(b)
@@ -424,8 +438,15 @@ class EncodecWrapper(Module):
         return self.decode_batch(emb)[0]
 
 
-GUIDANCE_PASSES = {'null': _lib.DROP_CLIP | _lib.DROP_CTX, 'drop_t5': _lib.DROP_CTX, 'drop_clip': _lib.DROP_CLIP,
-                   'drop_roll': _lib.DROP_ROLL}
+# 'null' is the reference's CFG pass (X3:2104: drop_audio_cond, drop_text_cond, drop_text_prompt); the others compose its
+# public drop flags one at a time
+GUIDANCE_PASSES = {'null': _lib.DROP_CLIP | _lib.DROP_CTX | _lib.DROP_AUDIO, 'drop_t5': _lib.DROP_CTX, 'drop_clip': _lib.DROP_CLIP,
+                   'drop_roll': _lib.DROP_ROLL, 'drop_audio': _lib.DROP_AUDIO}
+
+
+def _weights_fingerprint(module):
+    """Cheap identity of a module's tensors: storage address + in-place version counter of every parameter / buffer."""
+    return tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in module.state_dict(keep_vars=True).items())
 
 
 class E2TTS(Module):
@@ -511,15 +532,23 @@ class E2TTS(Module):
 
     def engine(self) -> _Engine:
         """Repack the current parameters into libe2b (done once per load / device move / precision change)."""
-        if self._engine is not None and self._engine_precision != self.precision:
+        fp = (self.precision, _weights_fingerprint(self))
+        if self._engine is not None and self.__dict__.get('_engine_fp') != fp:
+            # precision switch, load_state_dict on a sub-module, EMA copy or any in-place edit (p.data.copy_, optimiser step):
+            # the packed bf16 copy inside libe2b is stale
             self._engine = None
         if self._engine is None:
             tensors = _named_tensors(self.transformer, 'transformer.')
-            for name in ('proj_in', 'to_pred', 'proj_frames'):
+            for name in ('proj_in', 'to_pred', 'proj_frames', 'cond_proj_in'):
                 m = getattr(self, name)
-                tensors[name + '.weight'], tensors[name + '.bias'] = m.weight, m.bias
+                if m is None:
+                    continue
+                tensors[name + '.weight'] = m.weight
+                if m.bias is not None:
+                    tensors[name + '.bias'] = m.bias
             self._engine = _Engine(self.transformer.engine_config(self.num_channels, self.precision), tensors, self.device)
             self._engine_precision = self.precision
+            self.__dict__['_engine_fp'] = fp
         return self._engine
 
     # ---- condition encoders (outside the hot path) -------------------------------------------------------
@@ -564,11 +593,18 @@ class E2TTS(Module):
 
     VIDEO_FEATURE_SUFFIX = {'clip_vit': '.generated.npz', 'clip_vit2': '.generated.clip_vit2.npz', 'clip_convnext': '.generated.clip_convnext.npz',
                             'dinov2': '.generated.dinov2.npz', 'mixed': '.generated.mixed.npz'}
+    # videos under the training set's root keep their features in a sibling directory instead (X3:1679-1691); the root is the
+    # reference author's path -- point it at a local copy of the dataset to reuse caches the reference wrote there
+    VGGSOUND_ROOT = '/ailab-train2/speech/zhanghaomin/VGGSound/'
+    VGGSOUND_FEATURE_DIR = {'clip_vit': '/feature/', 'clip_vit2': '/feature_clip_vit2/', 'clip_convnext': '/feature_clip_convnext/',
+                            'dinov2': '/feature_dinov2/', 'mixed': '/feature_mixed/'}
 
     def video_feature_path(self, video_path):
-        """Cache file of a clip's per-video-frame embeddings (X3:1692-1704)."""
+        """Cache file of a clip's per-video-frame embeddings (X3:1679-1704)."""
         if self.video_encoder not in self.VIDEO_FEATURE_SUFFIX:
             raise Exception('Invalid video_encoder ' + str(self.video_encoder))
+        if video_path.startswith(self.VGGSOUND_ROOT):
+            return video_path.replace('/video/', self.VGGSOUND_FEATURE_DIR[self.video_encoder]).replace('.mp4', '.npz')
         return video_path.replace('.mp4', self.VIDEO_FEATURE_SUFFIX[self.video_encoder])
 
     def encode_video(self, video_paths, l):
@@ -617,26 +653,86 @@ class E2TTS(Module):
         emb_dev = (torch.cat(embs, 0) if embs else torch.zeros(2, d)).to(device, non_blocking=True)
         meta_dev = torch.tensor(meta, dtype=torch.int64).to(device, non_blocking=True)
         dur_dev = torch.tensor(durs, dtype=torch.float64).to(device, non_blocking=True)
-        rc = _lib.lib().e2b_stage_clip(_lib.ptr(emb_dev), _lib.ptr(meta_dev), _lib.ptr(dur_dev), len(video_paths), l, d,
-                                       int(self.sampling_rate), int(self.frame_size), _lib.ptr(out), _lib.stream_ptr())
-        _lib.check(rc, None, 'e2b_stage_clip')
+        with torch.cuda.device(device):
+            rc = _lib.lib().e2b_stage_clip(_lib.ptr(emb_dev), _lib.ptr(meta_dev), _lib.ptr(dur_dev), len(video_paths), l, d,
+                                           int(self.sampling_rate), int(self.frame_size), _lib.ptr(out), _lib.stream_ptr(device))
+            _lib.check(rc, None, 'e2b_stage_clip')
         return out
 
     def encode_frames(self, x, l):
-        """5-frame sliding windows -> Video2RollNet -> sigmoid -> x3 repeat -> cut/pad to l (X3:1525-1555)."""
+        """Piano-roll stream Float[b, l, 51] from the grey-scale frame stack Float[b, 1, t, w, h] (X3:1525-1555; SURVEY.md 8f
+        N3): 5-frame clamped windows (csrc/frames.cu, replaces the reference's Python loop over t) -> the attached Video2RollNet
+        (third-party ResNet18+FPN, stays torch) -> sigmoid, x3 repeat, cut / zero-pad to l frames (one kernel)."""
         if self.video2roll_net is None:
             raise NotImplementedError('attach `video2roll_net` or pass frames as a precomputed roll Float[b, n, 51]')
         b, c, t, w, h = x.shape
         assert c == 1
-        idx = (torch.arange(t, device=x.device)[:, None] + torch.arange(-2, 3, device=x.device)[None, :]).clamp(0, t - 1)
-        win = x[:, 0][:, idx]                                      # b t 5 w h
-        roll = torch.sigmoid(self.video2roll_net(win.reshape(b * t, 5, w, h))).reshape(b, t, NOTES)
-        roll = roll.repeat_interleave(3, dim=1)
-        if roll.shape[1] > l:
-            roll = roll[:, :l]
-        elif roll.shape[1] < l:
-            roll = torch.cat((roll, torch.zeros(b, l - roll.shape[1], NOTES, device=x.device)), 1)
+        if x.device.type != 'cuda':
+            raise RuntimeError('E2TTS.encode_frames runs on CUDA tensors only: libe2b has no CPU path')
+        L = _lib.lib()
+        x = x.to(torch.float32).contiguous()
+        win = torch.empty(b * t, 5, w, h, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(L.e2b_frame_windows(_lib.ptr(x), _lib.ptr(win), b, t, w * h, 5, _lib.stream_ptr(x.device)), None, 'e2b_frame_windows')
+            logits = self.video2roll_net(win).to(torch.float32).contiguous()             # [b*t, 51]
+            assert tuple(logits.shape) == (b * t, NOTES), logits.shape
+            roll = torch.empty(b, l, NOTES, device=x.device, dtype=torch.float32)
+            _lib.check(L.e2b_roll_expand(_lib.ptr(logits), _lib.ptr(roll), b, t, l, NOTES, 3, _lib.stream_ptr(x.device)), None, 'e2b_roll_expand')
         return roll
+
+    FRAMES_RAW_SUFFIX = '.generated_frames_raw.2.npz'      # X3:1886
+    VIDEO_MULTI = 3.0                                        # latent frames per roll frame, X3:1931
+
+    @staticmethod
+    def encode_video_frames(video_paths, l, piano=True):
+        """Grey-scale frame stacks for the piano-roll net, from the reference's caches (static, host side; X3:1829-1991 --
+        `app.py:236` / `predict.py` call it as `E2TTS.encode_video_frames(video_paths, l, piano)`; the dataset collate calls it with
+        two arguments, trainer3:1377, hence the default).
+
+        Returns `(video_frames Float[b', 1, T, 100, 900], midis Float[b', l, 51])` on the CPU like the reference, or
+        `(None, None)` when no clip contributes (no piano clip, X3:1961-1962).  Clips that are None or not piano are *dropped*
+        from the batch, as in the reference.  The cache is the `.generated_frames_raw.2.npz` the reference writes next to the
+        video (arr_0 = frames [F, 100, 900, 1] fp32, arr_1 = duration in seconds, X3:1905); decoding the video itself (moviepy +
+        PIL) is outside the hot path, so a missing cache is an error here.  Frame k of the result is video frame
+        j = min(round(i / 24000 / (duration / F)), F - 1) for i = start, start + 960, ... (X3:1934-1940)."""
+        video_frames, video_lens = [], []
+        fsv = int(E2TTS.VIDEO_MULTI * 320)
+        want = math.floor(l / E2TTS.VIDEO_MULTI) + 1
+        for video_path in video_paths:
+            if video_path is None or not piano:                                      # X3:1872-1876, 1924-1928
+                video_lens.append(0)
+                continue
+            if isinstance(video_path, tuple):
+                video_path, start_sample, max_sample = video_path
+            else:
+                start_sample, max_sample = 0, None
+            raw_path = video_path.replace('.mp4', E2TTS.FRAMES_RAW_SUFFIX)
+            if not os.path.exists(raw_path):
+                raise RuntimeError(f'no cached frames at {raw_path}: decoding the video (moviepy / PIL) is outside the hot path -- run the '
+                                   'reference once to create the cache, or pass frames= / a precomputed roll to sample()')
+            data = np.load(raw_path)
+            frames_raw = torch.from_numpy(np.ascontiguousarray(data['arr_0'], dtype=np.float32))
+            duration = float(data['arr_1'].item())
+            F_ = frames_raw.shape[0]
+            if max_sample is None:
+                max_sample = int(duration * 24000)
+            idx = []
+            for i in range(start_sample, max_sample + fsv, fsv):
+                idx.append(min(round(i / 24000 / (duration / (F_ - 0))), F_ - 1))
+                if len(idx) >= want:
+                    break
+            picked = frames_raw[torch.tensor(idx, dtype=torch.long)]
+            video_frames.append(picked.unsqueeze(0))
+            video_lens.append(picked.shape[0])
+        if len(video_frames) == 0:
+            return None, None
+        t_max = max(want, max(video_lens))
+        for i, vf in enumerate(video_frames):
+            if vf.shape[1] < t_max:
+                video_frames[i] = torch.cat([vf, torch.zeros(1, t_max - vf.shape[1], *vf.shape[2:])], 1)
+        video_frames = torch.cat(video_frames, 0).permute(0, 4, 1, 2, 3)
+        midis = torch.zeros(video_frames.shape[0], l, NOTES)
+        return video_frames, midis
 
     # ---- sampling ----------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -677,15 +773,33 @@ class E2TTS(Module):
                 duration = torch.full((batch,), duration, device=device, dtype=torch.long)
         else:
             duration = lens
-        duration = torch.maximum(lens, duration.to(lens.device)).clamp(max=max_duration)
+        lens = lens.to(device)
+        duration = torch.maximum(lens, duration.to(device)).clamp(max=max_duration)
         assert duration.shape[0] == batch
         n = int(duration.amax())
-        if int(lens[0]) != int(duration[0]):                                         # X3:2224 (whole-batch switch on item 0)
-            raise NotImplementedError('audio-conditioned in-painting (lens < duration) is outside this path (SURVEY.md 8f N4)')
-        if n > cond_seq_len:
+        # X3:2224 / 2259: ONE switch for the whole batch, taken from item 0 -- lens < duration means audio-conditioned in-painting
+        inpaint = int(lens[0]) != int(duration[0])
+        if inpaint:
+            if self.cond_proj_in is None:
+                raise TypeError("'NoneType' object is not callable: in-painting (lens < duration) needs E2TTS(if_cond_proj_in=True), "
+                                "the reference fails the same way at X3:2034")
+            if self.audiocond_snr is not None:
+                raise IndexError('audiocond_snr is set: the reference raises here too (add_noise indexes the [b, n, d] condition with the '
+                                 '[b, n, 1] cond_mask, X3:2123/2214); sample with audiocond_snr=None')
+
+        # shapes the engine will read through raw pointers (the reference would raise a shape error from the first matmul / cat)
+        if text.shape[0] != batch or text.shape[-1] != self.dim_text:
+            raise ValueError(f'text must be Float[{batch}, n, {self.dim_text}], got {tuple(text.shape)}')
+        if cond.shape[-1] != self.num_channels:
+            raise ValueError(f'cond must be Float[b, n, {self.num_channels}], got {tuple(cond.shape)}')
+        if roll is not None and (roll.shape[0] != batch or roll.shape[-1] != NOTES):
+            raise ValueError(f'frames (piano roll) must be Float[{batch}, n, {NOTES}], got {tuple(roll.shape)}')
+        if text.shape[1] < min(n, cond_seq_len):
+            raise ValueError(f'text has {text.shape[1]} frames, the latents {cond_seq_len}')
+        if n > text.shape[1]:
             text = F.pad(text, (0, 0, 0, n - text.shape[1]))
-            if roll is not None:
-                roll = F.pad(roll, (0, 0, 0, n - roll.shape[1]))
+        if roll is not None and n > roll.shape[1]:
+            roll = F.pad(roll, (0, 0, 0, n - roll.shape[1]))
         clip = text[:, :n].to(device=device, dtype=torch.float32).contiguous()
         roll = None if roll is None else roll[:, :n].contiguous()
 
@@ -694,11 +808,17 @@ class E2TTS(Module):
             if prompt is None:
                 raise NotImplementedError('a prompt (or context=) is required: the shipped callers always pass one')
             prompt = list(prompt)
+            if len(prompt) != batch:
+                raise ValueError(f'{len(prompt)} prompts for a batch of {batch}')
             if video_drop_prompt is not None:
                 for b in range(batch):
                     if video_drop_prompt[b]:
                         prompt[b] = 'the sound of X X'                               # X3:2053-2056
             context, context_mask = self.encode_text_cached(prompt)
+        if context.ndim != 3 or context.shape[0] != batch or context.shape[-1] != self.dim:
+            raise ValueError(f'context must be Float[{batch}, nc, {self.dim}], got {tuple(context.shape)}')
+        if context_mask is not None and tuple(context_mask.shape) != tuple(context.shape[:2]):
+            raise ValueError(f'context_mask must be Bool{list(context.shape[:2])}, got {tuple(context_mask.shape)}')
         context = context.to(device=device, dtype=torch.float32).clone()
         if video_drop_prompt is not None:
             for b in range(batch):
@@ -718,11 +838,20 @@ class E2TTS(Module):
         flags = [0] + [GUIDANCE_PASSES[k] for k, _ in guidance]
         weights = [w for _, w in guidance]
 
+        cond = F.pad(cond, (0, 0, 0, n - cond_seq_len), value=0.)                    # X3:2212
+        if noise is not None and tuple(noise.shape) != tuple(cond.shape):
+            raise ValueError(f'noise must have the shape of the (padded) latents {tuple(cond.shape)}, got {tuple(noise.shape)}')
+
         eng = self.engine()
         eng.prepare(batch, n, nc, len(flags))
         eng.set_conditions(clip, roll, context.contiguous(), [int(v) for v in duration.tolist()], ctx_lens, flags)
+        cond_f = None
+        if inpaint:
+            # step_cond = where(cond_mask, cond, 0) enters every network call through cond_proj_in (X3:2228, 2029-2035; the null pass
+            # and clips flagged by audio_drop_prompt see zeros, X3:2016-2020); cond_mask = lens_to_mask(lens) (X3:2196, 2213)
+            cond_f = cond.to(torch.float32).contiguous()
+            eng.set_audio_cond(cond_f, [int(v) for v in lens.tolist()], audio_drop_prompt)
 
-        cond = F.pad(cond, (0, 0, 0, n - cond_seq_len), value=0.)                    # X3:2212
         y = torch.randn_like(cond) if noise is None else noise.to(device=device, dtype=cond.dtype).clone()   # X3:2248
         y = y.to(torch.float32).contiguous()
         t = torch.linspace(0, 1, steps, device=self.device)                          # X3:2250-2252
@@ -731,6 +860,8 @@ class E2TTS(Module):
         before = eng.launch_count()
         out = eng.sample(y, [float(v) for v in t.tolist()], weights, apg, keep_parallel_frac)
         self._last_launches = eng.launch_count() - before
+        if inpaint and steps < 2:                                                    # no Euler update to fold the select into
+            out = torch.where(lens_to_mask(lens, n)[..., None], cond_f, out)         # X3:2259-2260
 
         if exists(return_raw_output) and return_raw_output:                          # X3:2265-2266
             return out
@@ -767,6 +898,10 @@ class E2TTS(Module):
     def velocity(self, x, t, *, clip, context, context_mask=None, roll=None, lens=None, passes=('null',)):
         """All guidance-pass velocities at time t: Float[P, b, n, d] (one `transformer_with_pred_head` per pass, X3:1993)."""
         b, n, _ = x.shape
+        if x.shape[-1] != self.num_channels or tuple(clip.shape) != (b, n, self.dim_text) or context.ndim != 3 or context.shape[0] != b \
+                or context.shape[-1] != self.dim or (roll is not None and tuple(roll.shape) != (b, n, NOTES)):
+            raise ValueError(f'velocity: x {tuple(x.shape)}, clip {tuple(clip.shape)}, context {tuple(context.shape)} do not fit this model '
+                             f'(num_channels {self.num_channels}, dim_text {self.dim_text}, dim {self.dim})')
         flags = [0] + [GUIDANCE_PASSES[k] for k in passes]
         order = sorted(range(len(flags)), key=lambda i: (flags[i] & _lib.DROP_CTX) != 0)
         eng = self.engine()

@@ -66,8 +66,10 @@ class EncodecDecoderB200:
         b, t, _ = x.shape
         if y is None:
             y = torch.empty(b, t, co, device=x.device, dtype=torch.float32)
-        rc = _lib.lib().e2b_conv1d_cl(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(y), b, t, ci, co, k, co, flags, _lib.stream_ptr())
-        _lib.check(rc, None, 'e2b_conv1d_cl')
+        with torch.cuda.device(x.device):          # launch on the tensors' device, not the process's current one
+            rc = _lib.lib().e2b_conv1d_cl(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(y), b, t, ci, co, k, co, flags,
+                                          _lib.stream_ptr(x.device))
+            _lib.check(rc, None, 'e2b_conv1d_cl')
         return y
 
     def _named(self, name, x, flags, y=None):
@@ -92,9 +94,10 @@ class EncodecDecoderB200:
                     sk = None if sk is None else torch.cat((sk, sk.new_zeros(bp - bc, t, hh)))
                     o = torch.empty(bp, t, hh, device=x.device, dtype=torch.float32)
                 hbuf = torch.empty(2, hh, bp, device=x.device, dtype=torch.float32)
-                rc = _lib.lib().e2b_lstm_layer(_lib.ptr(g.contiguous()), _lib.ptr(whh), _lib.ptr(None if sk is None else sk.contiguous()), _lib.ptr(o),
-                                               _lib.ptr(hbuf), _lib.ptr(self.counter), bp, t, hh, _lib.stream_ptr())
-                _lib.check(rc, None, 'e2b_lstm_layer')
+                with torch.cuda.device(x.device):
+                    rc = _lib.lib().e2b_lstm_layer(_lib.ptr(g.contiguous()), _lib.ptr(whh), _lib.ptr(None if sk is None else sk.contiguous()), _lib.ptr(o),
+                                                   _lib.ptr(hbuf), _lib.ptr(self.counter), bp, t, hh, _lib.stream_ptr(x.device))
+                    _lib.check(rc, None, 'e2b_lstm_layer')
                 if bp != bc:
                     out[b0:b0 + bc] = o[:bc]
             inp = out
