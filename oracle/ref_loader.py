@@ -26,7 +26,20 @@ import types
 
 from . import third_party as tp
 
-REFERENCE_ROOT = os.environ.get('E2B_REFERENCE_ROOT', '/root/reference')
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'baseline', '_ref')
+
+
+def _pick_root():
+    """The reference tree itself (build container) or the files oracle/stage_reference.py staged under the git-ignored
+    baseline/_ref/ (what travels to the GPU box)."""
+    env = os.environ.get('E2B_REFERENCE_ROOT')
+    for root in ([env] if env else []) + ['/root/reference', _STAGED]:
+        if os.path.isfile(os.path.join(root, 'src', 'e2_tts_pytorch', 'e2_tts_crossatt3.py')):
+            return root
+    return env or '/root/reference'
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:
