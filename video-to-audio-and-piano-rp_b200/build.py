@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libe2b.so')
-SOURCES = ['gemm.cu', 'attention.cu', 'attention_f32.cu', 'elementwise.cu', 'melspec.cu', 'staging.cu', 'frames.cu', 'encodec.cu', 'engine.cu', 'prof.cu']
+SOURCES = ['gemm.cu', 'attention.cu', 'attention_v1.cu', 'attention_f32.cu', 'elementwise.cu', 'melspec.cu', 'staging.cu', 'frames.cu', 'encodec.cu', 'engine.cu', 'prof.cu']
 HEADERS = ['ptx.cuh', 'kernels.h', 'prof.h', os.path.join('..', '..', 'include', 'e2b.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC']
 

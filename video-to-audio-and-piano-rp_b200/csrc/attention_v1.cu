@@ -5,25 +5,23 @@
 //     out *= sigmoid(head_gate)[token, head]
 //
 // One persistent CTA per SM walks work items (128-query tile, head, batch item).  S = Q K^T lives in TMEM (two 128-column buffers), the softmax
-// warps read it with tcgen05.ld and write P (bf16 pairs) back into TMEM with tcgen05.st -- every warp into the first 16 of the
-// 32 S columns it owns -- and O += P V (A operand from TMEM, V^T from shared memory) accumulates in TMEM over all key tiles.
-// P never touches shared memory: no st.shared + fence.proxy.async (a MEMBAR) per tile, and the 64 KB the P buffers took
-// now deepen the K/V ring.  The key tile width `bk` is chosen per call (multiple of 16, <= 128) so that the tiles divide the
-// sequence evenly: N = 782 runs as 7 x 112 = 784 keys instead of 7 x 128 = 896 (12.5 % less MMA and MUFU work), the T5
-// cross-attention (8 keys) as one 16-key tile.  Because the soft-clamp bounds every logit to [-50, 50],
+// warps read it with tcgen05.ld, write P (bf16) into shared memory in the UMMA K-major SWIZZLE_128B layout, and
+// O += P V accumulates in TMEM over all key tiles.  Because the soft-clamp bounds every logit to [-50, 50],
 // exp(sim) cannot overflow or underflow in fp32/bf16, so no running maximum and no O rescaling is needed:
 // out = (sum_j exp(sim_j) v_j) / (sum_j exp(sim_j)) is evaluated directly.  q arrives pre-scaled by 64^-0.5 and
 // RoPE-rotated, k RoPE-rotated, V transposed ([d, keys]) -- all produced by the QKV GEMM epilogue (gemm.cu) -- so
 // both MMAs take plain K-major operands.
-#include <cstdlib>
-
 #include "kernels.h"
 #include "prof.h"
 #include "ptx.cuh"
 
+// ROUND-1 KERNEL, kept as the A/B baseline and fallback behind e2b_attention_impl = 1 (E2B_ATTN=v1): P goes through shared memory
+// (st.shared + fence.proxy.async per tile), fixed 128-key tiles.  The production kernel is attention_v2.cu.
 namespace e2b {
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
+namespace att_v1 {
 
 constexpr int ATT_SOFTMAX_WARPS = 16;      // 4 TMEM lane quarters x 4 column quarters of every S tile
 constexpr int ATT_THREADS = 128 + 32 * ATT_SOFTMAX_WARPS;
@@ -31,21 +29,21 @@ constexpr int ATT_THREADS = 128 + 32 * ATT_SOFTMAX_WARPS;
 // the HIGHEST warp ids on purpose: the scheduler arbitrates highest-warp-id-first (B300_MICROARCH.md), and with ids 0/1 they
 // were starved by the four busy softmax warps sharing their schedulers, delaying every TMA / MMA issue.
 constexpr int ATT_W_TMA = ATT_SOFTMAX_WARPS, ATT_W_MMA = ATT_SOFTMAX_WARPS + 1, ATT_W_ALLOC = ATT_SOFTMAX_WARPS + 2;
-constexpr int ATT_BQ = 128, ATT_BK = 128 /* widest key tile; the per-call width is AttnArgs::bk */, ATT_D = 64;
-constexpr int ATT_KV = 5;                       // K/V ring depth
+constexpr int ATT_BQ = 128, ATT_BK = 128, ATT_D = 64;
+constexpr int ATT_KV = 3;                       // K/V ring depth
 constexpr int ATT_ON = 80;                      // PV MMA N: 64 value channels + a ones row (col 64 = row sum of P) + 15 zero rows
 constexpr int ATT_VATOM = ATT_ON * 128;         // one V^T swizzle atom: 80 rows x 128 B (rows 64..79 are constants written once)
 constexpr int ATT_VSTAGE = 2 * ATT_VATOM;       // two 64-key atoms per 128-key tile
 constexpr int ATT_SQ = 0;                       // 2 x 16 KB  Q   [128 q, 64 d]        (double-buffered across work items)
 constexpr int ATT_SK = 2 * 16384;               // ATT_KV x 16 KB  K   [128 keys, 64 d]
 constexpr int ATT_SV = ATT_SK + ATT_KV * 16384; // ATT_KV x 20 KB  V^T 2 x [80 rows, 64 keys]
-constexpr int ATT_BAR = ATT_SV + ATT_KV * ATT_VSTAGE;
+constexpr int ATT_SP = ATT_SV + ATT_KV * ATT_VSTAGE; // 2 x 32 KB  P   2 x [128 q, 64 keys]
+constexpr int ATT_BAR = ATT_SP + 2 * 32768;
 constexpr int ATT_LENS = ATT_BAR + 256;          // clamped kv length of every kv sequence of the call
 constexpr int ATT_MAXB = 1024;                  // more kv sequences than this: lengths are read from global memory instead
 constexpr int ATT_SMEM = ATT_LENS + ATT_MAXB * 4;
 static_assert(ATT_SMEM <= 232448, "shared memory budget");
-constexpr uint32_t ATT_TMEM_COLS = 512;         // S0 @0, S1 @128 (P aliased: key columns 32c..32c+31 of a tile -> TMEM columns 32c..32c+15),
-                                                // O0 @256, O1 @336 (80 columns each)
+constexpr uint32_t ATT_TMEM_COLS = 512;         // S0 @0, S1 @128, O0 @256, O1 @336 (80 columns each)
 constexpr uint32_t ATT_TMEM_O = 256;
 
 // Soft-clamp + exponent in one polynomial.  With w = z^2 and |z| / clamp < 0.5,
@@ -62,12 +60,12 @@ __device__ __forceinline__ float softclamp_exp2_arg_exact(float z, float ex_a, f
 
 // p = 2^(z * poly(z^2)) for the 32 logits of one warp-tile, packed to bf16 pairs, in packed-pair arithmetic (FFMA2 / FMUL2:
 // half the issue slots of the scalar forms).  HI selects the degree-9 series.
-template <bool HI, int NP>
+template <bool HI>
 __device__ __forceinline__ void exp_block(const uint32_t (&v)[32], const ClampPoly& cp, uint32_t (&pk)[16]) {
   const uint64_t c0 = f32x2_pack(cp.c0, cp.c0), c1 = f32x2_pack(cp.c1, cp.c1), c2 = f32x2_pack(cp.c2, cp.c2);
   const uint64_t c3 = f32x2_pack(cp.c3, cp.c3), c4 = f32x2_pack(cp.c4, cp.c4);
 #pragma unroll
-  for (int i = 0; i < NP; ++i) {
+  for (int i = 0; i < 16; ++i) {
     const uint64_t z = f32x2_pack(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
     const uint64_t w = f32x2_mul(z, z);
     uint64_t q;
@@ -89,7 +87,6 @@ struct AttnArgs {
   CUtensorMap tmQ, tmK, tmV;
   e2b_attn_desc d;
   ClampPoly cp;
-  int bk;                      // key tile width of this call (multiple of 16, <= ATT_BK); the K tensor map's box has bk rows
   long long* dbg;
 };
 
@@ -115,7 +112,7 @@ struct ItemCursor {          // iterates the (item, kv-tile) sequence of this CT
 // kv_lens global load whose destination register was spilled, i.e. waited for at once) costing ~2K cycles per item.
 struct ItemWalk {
   ItemCursor c;
-  int dq, dh, db, dkvb, bk;
+  int dq, dh, db, dkvb;
   const int* lens;           // shared memory, [kv batches] (null: more than ATT_MAXB sequences, read global memory)
 };
 __device__ __forceinline__ int clamped_kv_len(const e2b_attn_desc& d, int kvb) {
@@ -127,11 +124,10 @@ __device__ __forceinline__ void cursor_fetch(ItemWalk& w, const e2b_attn_desc& d
   c.valid = c.item < total;
   c.j = 0;
   c.kv_len = !c.valid ? 0 : w.lens ? w.lens[c.kvb] : clamped_kv_len(d, c.kvb);
-  c.nt = max(1, (c.kv_len + w.bk - 1) / w.bk);            // at least one (fully masked) tile so O is defined
+  c.nt = max(1, (c.kv_len + ATT_BK - 1) / ATT_BK);        // at least one (fully masked) tile so O is defined
 }
-__device__ __forceinline__ void walk_init(ItemWalk& w, const e2b_attn_desc& d, int qtiles, int total, const int* lens, int bk) {
+__device__ __forceinline__ void walk_init(ItemWalk& w, const e2b_attn_desc& d, int qtiles, int total, const int* lens) {
   const int g = gridDim.x;
-  w.bk = bk;
   w.dq = g % qtiles;
   const int gh = g / qtiles;
   w.dh = gh % d.heads;
@@ -184,21 +180,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   uint64_t* q_full = bars;            // [2]
   uint64_t* q_empty = bars + 2;       // [2]
   uint64_t* o_full = bars + 4;        // [2]
-  uint64_t* o_empty = bars + 6;       // [2] (one arrival per softmax warp)
-  uint64_t* s_full = bars + 8;        // [2] S(g) complete in TMEM buffer g & 1
-  uint64_t* p_full = bars + 10;       // [2] (one arrival per softmax warp) P(g) written over S(g)
-  uint64_t* p_empty = bars + 12;      // [2] PV(g) complete: TMEM buffer g & 1 may take S(g + 2)
-  uint64_t* kv_full = bars + 14;      // [ATT_KV]
-  uint64_t* kv_empty = bars + 14 + ATT_KV;   // [ATT_KV]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14 + 2 * ATT_KV);
+  uint64_t* o_empty = bars + 6;       // [2] (all softmax threads arrive)
+  uint64_t* s_full = bars + 8;        // [2]
+  uint64_t* s_empty = bars + 10;      // [2] (all softmax threads arrive)
+  uint64_t* p_full = bars + 12;       // [2] (all softmax threads arrive)
+  uint64_t* p_empty = bars + 14;      // [2]
+  uint64_t* kv_full = bars + 16;      // [ATT_KV]
+  uint64_t* kv_empty = bars + 16 + ATT_KV;   // [ATT_KV]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16 + 2 * ATT_KV);
 
   const e2b_attn_desc& d = args.d;
-  const int bk = args.bk;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qtiles = (d.q_rows_per_batch + ATT_BQ - 1) / ATT_BQ;
   const int total = qtiles * d.heads * d.batch;
   // One elected arrival per softmax warp (after __syncwarp): mbarrier arrivals are lane-serialised shared-memory atomics, and
-  // 512 per-thread arrivals per S tile sat on the critical path (ncu: warps spinning on s_full, no pipe busy).
+  // 512 per-thread arrivals on two barriers per S tile sat on the critical path (ncu: warps spinning on s_full, no pipe busy).
   constexpr uint32_t NSOFT = ATT_SOFTMAX_WARPS;
 
   if (warp == ATT_W_TMA && lane == 0) {
@@ -213,6 +209,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       mbar_init(&o_full[s], 1);
       mbar_init(&o_empty[s], NSOFT);
       mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], NSOFT);
       mbar_init(&p_full[s], NSOFT);
       mbar_init(&p_empty[s], 1);
     }
@@ -249,28 +246,27 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const bool two_atoms = bk > 64;                     // keys 64.. of a tile live in the second V^T atom
 
   // Producer / issuer roles run on their whole warp with uniform control flow; only the TMA / MMA / commit instructions are
   // under elect_one() (a `lane == 0` role branch makes the compiler wrap every UTCHMMA / UTMALDG in a divergence loop).
   if (warp == ATT_W_TMA) {
     // ------------------------------------------------------------ TMA producer
     // The K/V working set of a call (hundreds of MB) does not live in L2, and a tile can only be requested into shared
-    // memory once its ring slot is free, i.e. at most ATT_KV tiles ahead.  A second cursor therefore runs ATT_PF tiles further
-    // ahead and asks the TMA unit to pull those tiles into L2 (no shared-memory cost), so the real loads are L2 hits.
+    // memory once its ring slot is free, i.e. at most ATT_KV tiles ahead: measured ~3.9K cycles from issue to landing, which
+    // set the whole kernel's pace.  A second cursor therefore runs ATT_PF tiles further ahead and asks the TMA unit to pull
+    // those tiles into L2 (no shared-memory cost), so the real loads are L2 hits.
     constexpr int ATT_PF = 6;
     ItemWalk wc, wpf;
-    walk_init(wc, d, qtiles, total, lens_s, bk);
-    walk_init(wpf, d, qtiles, total, lens_s, bk);
+    walk_init(wc, d, qtiles, total, lens_s);
+    walk_init(wpf, d, qtiles, total, lens_s);
     ItemCursor& c = wc.c;
     ItemCursor& pf = wpf.c;
-    const uint32_t kv_bytes = (uint32_t)bk * 128u + (two_atoms ? 16384u : 8192u);
     auto prefetch_tile = [&](const ItemCursor& t) {
       if (t.j == 0) tma_prefetch_l2_2d(&args.tmQ, d.q_col0 + t.h * ATT_D, t.b * d.q_rows_per_batch + t.qt * ATT_BQ);
-      tma_prefetch_l2_2d(&args.tmK, d.k_col0 + t.h * ATT_D, t.kvb * d.kv_rows_per_batch + t.j * bk);
+      tma_prefetch_l2_2d(&args.tmK, d.k_col0 + t.h * ATT_D, t.kvb * d.kv_rows_per_batch + t.j * ATT_BK);
       const int vr = (t.kvb * d.heads + t.h) * ATT_D;
-      tma_prefetch_l2_2d(&args.tmV, t.j * bk, vr);
-      if (two_atoms) tma_prefetch_l2_2d(&args.tmV, t.j * bk + 64, vr);
+      tma_prefetch_l2_2d(&args.tmV, t.j * ATT_BK, vr);
+      tma_prefetch_l2_2d(&args.tmV, t.j * ATT_BK + 64, vr);
     };
     for (int i = 0; i < ATT_PF + ATT_KV && pf.valid; ++i) {
       if (elect_one()) prefetch_tile(pf);
@@ -291,10 +287,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         const int s = g % ATT_KV;
         mbar_wait(&kv_empty[s], ((g / ATT_KV) & 1) ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&kv_full[s], kv_bytes);
-          tma_load_2d(smem + ATT_SK + s * 16384, &args.tmK, &kv_full[s], d.k_col0 + c.h * ATT_D, c.kvb * d.kv_rows_per_batch + j * bk);
-          tma_load_2d(smem + ATT_SV + s * ATT_VSTAGE, &args.tmV, &kv_full[s], j * bk, vrow);
-          if (two_atoms) tma_load_2d(smem + ATT_SV + s * ATT_VSTAGE + ATT_VATOM, &args.tmV, &kv_full[s], j * bk + 64, vrow);
+          mbar_arrive_expect_tx(&kv_full[s], 32768);
+          tma_load_2d(smem + ATT_SK + s * 16384, &args.tmK, &kv_full[s], d.k_col0 + c.h * ATT_D, c.kvb * d.kv_rows_per_batch + j * ATT_BK);
+          tma_load_2d(smem + ATT_SV + s * ATT_VSTAGE, &args.tmV, &kv_full[s], j * ATT_BK, vrow);
+          tma_load_2d(smem + ATT_SV + s * ATT_VSTAGE + ATT_VATOM, &args.tmV, &kv_full[s], j * ATT_BK + 64, vrow);
           if (pf.valid) prefetch_tile(pf);
         }
         __syncwarp();
@@ -307,15 +303,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     // Two issuing threads (this one and the PV issuer below) in different warps / schedulers: a clock64 timeline showed a single
     // thread needs ~1000 cycles to issue one PV group (8 tcgen05.mma + commits), ~350 for one S group and ~90 per mbarrier
     // probe -- ~3K cycles of serial work per tile, which (not the softmax, ~1.9K) set the kernel's pace.
-    const uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, (uint32_t)bk);
+    constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, ATT_BK);
     ItemWalk ws;
-    walk_init(ws, d, qtiles, total, lens_s, bk);
+    walk_init(ws, d, qtiles, total, lens_s);
     ItemCursor& cs = ws.c;
     for (int gs = 0; cs.valid; ++gs) {
       const int sb = gs & 1, ks = gs % ATT_KV, qb = cs.it & 1;
       if (cs.j == 0) mbar_wait(&q_full[qb], (cs.it >> 1) & 1);
       mbar_wait(&kv_full[ks], (gs / ATT_KV) & 1);
-      // TMEM buffer sb holds S(g-2) and then P(g-2) in the same columns: it is free once PV(g-2) has read P(g-2)
+      mbar_wait(&s_empty[sb], ((gs >> 1) & 1) ^ 1);
+      // S(g) and P(g) share the buffer index: waiting here for PV(g-2) to have consumed P(g-2) lets the softmax warps write
+      // P(g) as soon as they see s_full(g), without a second mbarrier probe (~240 cycles each even when already complete)
       mbar_wait(&p_empty[sb], ((gs >> 1) & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
@@ -333,11 +331,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       walk_next_tile(ws, d, qtiles, total);
     }
   } else if (warp == ATT_W_ALLOC) {
-    // ------------------------------------------------------------ O += P V issuer (A = P from TMEM, B = V^T from shared memory)
+    // ------------------------------------------------------------ O += P V issuer
     constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, ATT_ON);
-    const int ksteps = bk / 16;
     ItemWalk wp;
-    walk_init(wp, d, qtiles, total, lens_s, bk);
+    walk_init(wp, d, qtiles, total, lens_s);
     ItemCursor& cp = wp.c;
     for (int gp = 0; cp.valid; ++gp) {
       const int pb = gp & 1, ks = gp % ATT_KV, ob = cp.it & 1;
@@ -345,21 +342,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       if (cp.j == 0) mbar_wait(&o_empty[ob], ((cp.it >> 1) & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
-        dbg_stamp(gp, 2);
-        const uint32_t tmem_o = tmem_base + ATT_TMEM_O + ob * ATT_ON;
-        const uint32_t tmem_p = tmem_base + pb * ATT_BK;
-        const uint64_t dv0 = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SV + ks * ATT_VSTAGE));
-        for (int kk = 0; kk < ksteps; ++kk) {
-          // P: keys 16kk..16kk+15 are 8 TMEM columns inside the 16 the owning softmax warp wrote: 32 (kk / 2) + 8 (kk % 2)
-          // V^T: atom (kk >> 2) is +10 KB (encoded >> 4), then 32 B per 16-key step inside the swizzle atom
-          const uint32_t ta = tmem_p + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8);
-          const uint64_t dv = dv0 + (uint64_t)((kk >> 2) * (ATT_VATOM >> 4) + (kk & 3) * UMMA_K_STEP_ENC);
-          umma_bf16_ts(tmem_o, ta, dv, idesc_o, (cp.j | kk) != 0 ? 1u : 0u);
-        }
-        umma_commit(&kv_empty[ks]);      // S(g) finished long before P(g) existed, so this also covers K of the slot
-        umma_commit(&p_empty[pb]);
-        if (cp.j == cp.nt - 1) umma_commit(&o_full[ob]);
-        dbg_stamp(gp, 3);
+      dbg_stamp(gp, 2);
+      const uint32_t tmem_o = tmem_base + ATT_TMEM_O + ob * ATT_ON;
+      const uint64_t dp0 = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SP + pb * 32768));
+      const uint64_t dv0 = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SV + ks * ATT_VSTAGE));
+#pragma unroll
+      for (int kk = 0; kk < ATT_BK / 16; ++kk) {
+        // atom (kk >> 2): +16 KB for P, +10 KB for V^T (encoded >> 4); then 32 B per 16-key step inside the swizzle atom
+        const uint64_t dp = dp0 + (uint64_t)((kk >> 2) * (16384 >> 4) + (kk & 3) * UMMA_K_STEP_ENC);
+        const uint64_t dv = dv0 + (uint64_t)((kk >> 2) * (ATT_VATOM >> 4) + (kk & 3) * UMMA_K_STEP_ENC);
+        umma_bf16_ss(tmem_o, dp, dv, idesc_o, (cp.j | kk) != 0 ? 1u : 0u);
+      }
+      umma_commit(&kv_empty[ks]);      // S(g) finished long before P(g) existed, so this also covers K of the slot
+      umma_commit(&p_empty[pb]);
+      if (cp.j == cp.nt - 1) umma_commit(&o_full[ob]);
+      dbg_stamp(gp, 3);
       }
       __syncwarp();
       walk_next_tile(wp, d, qtiles, total);
@@ -374,9 +371,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     const uint32_t lane_base = uint32_t(quarter * 32) << 16;
     const ClampPoly cp = args.cp;
     const int c0 = cq * 32;                             // first key column of this warp inside the tile
-    const bool col_live = c0 < bk;                      // with bk < 128 the last column quarters of a tile do not exist
+    // P: keys c0..c0+31 live in swizzle atom (cq >> 1), 16-byte chunks ((cq & 1) * 4 + q) ^ (r & 7) of the 128-byte row
+    const uint32_t p_off = (cq >> 1) * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
     ItemWalk wk;
-    walk_init(wk, d, qtiles, total, lens_s, bk);
+    walk_init(wk, d, qtiles, total, lens_s);
     ItemCursor& c = wk.c;
     // Deferred item epilogue: O of item i is read out after the FIRST tile of item i+1, when its last PV has long completed,
     // so the o_full wait and the stores are off the critical path (O and Q are double-buffered across items).
@@ -423,76 +421,59 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       for (int j = 0; j < c.nt; ++j, ++g) {
         const int s = g & 1;
         const uint32_t ph = (g >> 1) & 1;
-        const int nvalid = min(bk, c.kv_len - j * bk);  // live keys of this tile
+        const int nvalid = min(ATT_BK, c.kv_len - j * ATT_BK);
         if (warp == 0 && lane == 0) dbg_stamp(g, 5);
-        mbar_wait(&s_full[s], ph);
+        mbar_wait(&s_full[s], ph);          // also guarantees that P buffer s is free (the S issuer waited for p_empty)
         tc_fence_after();
         if (warp == 0 && lane == 0) dbg_stamp(g, 6);
-        const uint32_t t_blk = tmem_base + lane_base + s * ATT_BK + c0;     // this warp's 32 S columns; P goes to the first 16
-        if (col_live) {
-          const int ncol = nvalid - c0;                 // live logits of this warp's block (<= 0: none)
-          uint32_t pk[16];
-          if (warp_valid && ncol > 0) {
-            // One 32-column block per warp and tile: the polynomial (FMA pipe) and ex2 (MUFU pipe, 16/clk/SM: the binding unit of
-            // this kernel, tools/pipe_bench.cu) streams of the logits sit in ONE basic block per tier so that they interleave.
-            // A block with at most 16 live logits (the last column quarter at bk = 112, the 8..16-key cross-attention tile) only
-            // computes its first half: the MUFU pipe is shared by the four warps of a scheduler.
-            uint32_t v[32];
-            tmem_ld32(t_blk, v);
-            tmem_ld_wait();
-            if (ncol < 32) {                            // columns past the last key hold stale TMEM: take them out of the tier test
+        uint8_t* prow = smem + ATT_SP + s * 32768 + p_off;
+        const bool live = warp_valid && c0 < nvalid;
+        uint32_t pk[16];
+        if (live) {
+          // One 32-column block per warp and tile: the polynomial (FMA pipe) and ex2 (MUFU pipe, 16/clk/SM: the binding unit of
+          // this kernel, tools/pipe_bench.cu) streams of the 32 logits sit in ONE basic block per tier so that they interleave;
+          // as two 16-column halves separated by the tier branch the four warps of a scheduler ran their FMA and MUFU phases in
+          // lockstep, back to back (timeline: 1850 clk per tile for 1024 clk of MUFU work).
+          uint32_t v[32];
+          tmem_ld32(tmem_base + lane_base + s * ATT_BK + c0, v);
+          tmem_ld_wait();
+          float wm = 0.f;
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i >= ncol) v[i] = 0u;
-            }
-            float wm = 0.f;
+          for (int i = 0; i < 32; ++i) wm = fmaxf(wm, fabsf(__uint_as_float(v[i])));
+          if (!__any_sync(0xffffffffu, wm > cp.wlo)) {
+            exp_block<false>(v, cp, pk);                  // |z/clamp| <= 0.16: degree-5 series exact to 1e-5 in the exponent
+          } else if (!__any_sync(0xffffffffu, wm * wm >= cp.wmax)) {
+            exp_block<true>(v, cp, pk);
+          } else {                                        // rare: logits beyond the series' range -> exact tanh for the block
 #pragma unroll
-            for (int i = 0; i < 32; ++i) wm = fmaxf(wm, fabsf(__uint_as_float(v[i])));
-            const bool lo = !__any_sync(0xffffffffu, wm > cp.wlo);
-            const bool hi = !lo && !__any_sync(0xffffffffu, wm * wm >= cp.wmax);
-            if (ncol > 16) {
-              if (lo) {
-                exp_block<false, 16>(v, cp, pk);        // |z/clamp| <= 0.16: degree-5 series exact to 1e-5 in the exponent
-              } else if (hi) {
-                exp_block<true, 16>(v, cp, pk);
-              } else {                                  // rare: logits beyond the series' range -> exact tanh for the block
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  pk[i] = pack_bf16(ex2_approx(softclamp_exp2_arg_exact(__uint_as_float(v[2 * i]), cp.ex_a, cp.ex_b)),
-                                    ex2_approx(softclamp_exp2_arg_exact(__uint_as_float(v[2 * i + 1]), cp.ex_a, cp.ex_b)));
-              }
-            } else {
-#pragma unroll
-              for (int i = 8; i < 16; ++i) pk[i] = 0u;
-              if (lo) {
-                exp_block<false, 8>(v, cp, pk);
-              } else if (hi) {
-                exp_block<true, 8>(v, cp, pk);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  pk[i] = pack_bf16(ex2_approx(softclamp_exp2_arg_exact(__uint_as_float(v[2 * i]), cp.ex_a, cp.ex_b)),
-                                    ex2_approx(softclamp_exp2_arg_exact(__uint_as_float(v[2 * i + 1]), cp.ex_a, cp.ex_b)));
-              }
-            }
-            if (ncol < 32) {                            // ragged last tile: keys beyond kv_len contribute exactly zero
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const uint32_t keep = (2 * i + 1 < ncol) ? 0xffffffffu : (2 * i < ncol) ? 0x0000ffffu : 0u;
-                pk[i] &= keep;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+            for (int i = 0; i < 16; ++i)
+              pk[i] = pack_bf16(ex2_approx(softclamp_exp2_arg_exact(__uint_as_float(v[2 * i]), cp.ex_a, cp.ex_b)),
+                                ex2_approx(softclamp_exp2_arg_exact(__uint_as_float(v[2 * i + 1]), cp.ex_a, cp.ex_b)));
           }
-          tmem_st16(t_blk, pk);                         // P over the first 16 of the 32 columns this warp has just read
-          tmem_st_wait();
+          if (c0 + 32 > nvalid) {                          // ragged last tile: keys beyond kv_len contribute exactly zero
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t keep = (c0 + 2 * i + 1 < nvalid) ? 0xffffffffu : (c0 + 2 * i < nvalid) ? 0x0000ffffu : 0u;
+              pk[i] &= keep;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((cq & 1) * 4 + q) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
         if (warp == 0 && lane == 0) dbg_stamp(g, 0);
-        tc_fence_before();             // this lane's tcgen05.ld / tcgen05.st are complete: order them before the arrival
+        tc_fence_before();             // this lane's tcgen05.ld of S are complete (tcgen05.wait::ld above)
+        fence_proxy_async_smem();      // this lane's P stores are visible to the async proxy (tensor core)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[s]);
+        if (lane == 0) {
+          mbar_arrive(&s_empty[s]);
+          mbar_arrive(&p_full[s]);
+        }
         if (j == 0 && pend.valid) {    // previous item's O: its last PV completed during this tile
           flush(pend);
           pend.valid = false;
@@ -514,29 +495,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   if (warp == ATT_W_ALLOC) tmem_dealloc(tmem_base, ATT_TMEM_COLS);
 }
 
+}  // namespace att_v1
 }  // namespace e2b
 
 using namespace e2b;
+using namespace e2b::att_v1;
 
-extern "C" int e2b_attention_set_debug(long long* dev_buf) {
-  e2b::g_att_dbg_host = dev_buf;
-  return 0;
-}
-
-// > 0: use this key tile width instead of the per-call choice (A/B tests: 128 = the fixed tiling of round 1)
-extern "C" { int e2b_attention_force_bk = 0; }
-// 0: this kernel; 1: the round-1 kernel (attention_v1.cu).  Initialised from the environment (E2B_ATTN=v1) on first use.
-extern "C" { int e2b_attention_impl = -1; }
-extern "C" int e2b_attention_v1_launch(const e2b_attn_desc* d, cudaStream_t stream);
-
-extern "C" int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream) {
-  if (e2b_attention_impl < 0) {
-    const char* e = getenv("E2B_ATTN");
-    e2b_attention_impl = (e && (e[0] == 'v' ? e[1] == '1' : e[0] == '1')) ? 1 : 0;
-    const char* f = getenv("E2B_ATTN_BK");
-    if (f && atoi(f) > 0) e2b_attention_force_bk = atoi(f);
-  }
-  if (e2b_attention_impl == 1) return e2b_attention_v1_launch(d, stream);
+extern "C" int e2b_attention_v1_launch(const e2b_attn_desc* d, cudaStream_t stream) {
   if (d->batch <= 0 || d->heads <= 0 || d->q_rows_per_batch <= 0) return 0;
   if (d->kv_rows_per_batch <= 0) { e2b_set_kernel_error("attention: kv_rows_per_batch must be positive"); return -1; }
   if ((d->ldo % 8) || (reinterpret_cast<uintptr_t>(d->out) & 15)) { e2b_set_kernel_error("attention: out must be 16-byte aligned"); return -1; }
@@ -560,16 +525,7 @@ extern "C" int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream)
   const int kv_batches = d->kv_batch_mod > 0 ? d->kv_batch_mod : d->batch;
   const uint64_t k_rows = (uint64_t)kv_batches * d->kv_rows_per_batch;
   if (make_tmap_bf16(&a.tmQ, d->q, q_rows, (uint64_t)d->q_col0 + d->heads * 64, d->ldq, ATT_BQ)) return -1;
-  {
-    // key tile width: the smallest multiple of 16 that covers the sequence in the same number of tiles as 128-wide ones
-    const int tiles = (d->kv_rows_per_batch + ATT_BK - 1) / ATT_BK;
-    const int per = (d->kv_rows_per_batch + tiles - 1) / tiles;
-    a.bk = (per + 15) / 16 * 16;
-    if (a.bk > ATT_BK) a.bk = ATT_BK;
-    if (e2b_attention_force_bk > 0) a.bk = e2b_attention_force_bk;
-    if (a.bk < 16 || a.bk > ATT_BK || a.bk % 16) { e2b_set_kernel_error("attention: key tile width %d must be a multiple of 16 in [16,128]", a.bk); return -1; }
-  }
-  if (make_tmap_bf16(&a.tmK, d->k, k_rows, (uint64_t)d->k_col0 + d->heads * 64, d->ldk, (uint32_t)a.bk)) return -1;
+  if (make_tmap_bf16(&a.tmK, d->k, k_rows, (uint64_t)d->k_col0 + d->heads * 64, d->ldk, ATT_BK)) return -1;
   if (make_tmap_bf16(&a.tmV, d->vt, (uint64_t)kv_batches * d->heads * 64, d->kv_rows_per_batch, d->vt_ld, 64)) return -1;
   static bool configured[E2B_MAX_DEVICES] = {false};
   bool& conf = configured[e2b_device_slot()];
@@ -581,7 +537,7 @@ extern "C" int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream)
   const long long items = (long long)((d->q_rows_per_batch + ATT_BQ - 1) / ATT_BQ) * d->heads * d->batch;
   const int sms = e2b_num_sms();
   dim3 grid((unsigned)(items < sms ? items : sms));
-  ProfScope ps(stream, "attention", (long long)d->batch * d->q_rows_per_batch, d->kv_rows_per_batch, d->heads,
+  ProfScope ps(stream, "attention_v1", (long long)d->batch * d->q_rows_per_batch, d->kv_rows_per_batch, d->heads,
                4.0 * d->batch * d->heads * (double)d->q_rows_per_batch * d->kv_rows_per_batch * 64.0,
                2.0 * d->batch * d->heads * 64.0 * (2.0 * d->q_rows_per_batch + 2.0 * d->kv_rows_per_batch));
   attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(a);
