@@ -143,3 +143,33 @@ def test_qkv_epilogue_rope_vt_gate():
     assert rel(vt[:, :Nseq], vref) < 5e-3
     assert torch.count_nonzero(vt[:, Nseq:]) == 0
     assert rel(hg, torch.sigmoid(gt + hb)) < 1e-4
+    # v as plain rows (the MN-major operand of the current attention kernel) + a wider N with a ragged last tile that only
+    # holds the head-gate columns (the narrow-MMA path: N = 3 * 128 + 2 -> tiles of 256 | 130 valid columns)
+    vrows = torch.full((M + 1, HD), -3.0, device=DEV, dtype=torch.bfloat16)
+    qk2, hg2 = torch.zeros_like(qk), torch.zeros_like(hg)
+    gemm(M, 3 * HD + H, C, [a], w, _lib.EPI_QKV, out=qk2, ldo=2 * HD, q_end=HD, k_end=2 * HD, v_end=3 * HD, q_scale=0.125,
+         rope=rope, pos_off=7, rows_per_batch=Nseq, vt=vrows, vt_ld=HD, heads_v=H, hgate=hg2, hgate_ld=H, hgate_bias=hb, v_rowmajor=1)
+    assert torch.equal(qk2, qk) and torch.equal(hg2, hg)
+    assert rel(vrows[:M], v) < 5e-3 and (vrows[M] == -3.0).all()
+    assert torch.equal(vrows[:M].reshape(B, Nseq, H, 64).permute(0, 2, 3, 1).reshape(B * H * 64, Nseq), vt[:, :Nseq])
+
+
+@pytest.mark.parametrize('H', [4, 8, 16])
+def test_qkv_ragged_last_tile_uses_narrow_mma(H):
+    """N = 3 H 64 + H: for H = 4 (N = 772) and 16 (N = 3088) the last 256-column tile holds only the H gate columns; its MMA runs
+    16 (rounded-up) columns wide.  Every column of the result must still be right."""
+    Nseq, B, C = 150, 2, 256
+    HD, M = H * 64, B * Nseq
+    g = torch.Generator().manual_seed(H)
+    a = bf(torch.randn(M, C, generator=g)).to(DEV)
+    w = bf(torch.randn(3 * HD + H, C, generator=g) / math.sqrt(C)).to(DEV)
+    hb = torch.randn(H, generator=g).to(DEV)
+    rope = torch.stack((torch.ones(Nseq, 32), torch.zeros(Nseq, 32)), -1).to(DEV).contiguous()      # identity rotation
+    qk = torch.zeros(M, 2 * HD, device=DEV, dtype=torch.bfloat16)
+    vrows = torch.zeros(M, HD, device=DEV, dtype=torch.bfloat16)
+    hg = torch.zeros(M, H, device=DEV)
+    gemm(M, 3 * HD + H, C, [a], w, _lib.EPI_QKV, out=qk, ldo=2 * HD, q_end=HD, k_end=2 * HD, v_end=3 * HD, q_scale=1.0, rope=rope, pos_off=0,
+         rows_per_batch=Nseq, vt=vrows, vt_ld=HD, heads_v=H, hgate=hg, hgate_ld=H, hgate_bias=hb, v_rowmajor=1)
+    full = a.float() @ w.float().t()
+    assert rel(qk, full[:, :2 * HD]) < 5e-3 and rel(vrows, full[:, 2 * HD:3 * HD]) < 5e-3
+    assert rel(hg, torch.sigmoid(full[:, 3 * HD:] + hb)) < 1e-4

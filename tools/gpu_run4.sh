@@ -1,0 +1,8 @@
+set -x
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_1_gemm.py tests/test_gpu_2_attention.py tests/test_gpu_4_path.py -m gpu -q > gpurun_out/r2_tests4.log 2>&1; echo "pytest exit $?" >> gpurun_out/r2_tests4.log
+tail -3 gpurun_out/r2_tests4.log
+python bench.py --no-cpu-baseline --profile-out gpurun_out/r2_prof4.json > gpurun_out/r2_bench4.json 2> gpurun_out/r2_bench4.err
+python tools/prof_forward.py --batch 64 > gpurun_out/r2_ncu4_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"gemm_kernel|attention_kernel|dwconv|rmsnorm" -s 14 -c 31 -o gpurun_out/r2_prof_layer python tools/prof_forward.py --batch 64 > gpurun_out/r2_ncu4.log 2>&1
+tail -3 gpurun_out/r2_ncu4.log

@@ -8,9 +8,8 @@
 // warps read it with tcgen05.ld and write P (bf16 pairs) back into TMEM with tcgen05.st -- every warp into the first 16 of the
 // 32 S columns it owns -- and O += P V (A operand from TMEM, V^T from shared memory) accumulates in TMEM over all key tiles.
 // P never touches shared memory: no st.shared + fence.proxy.async (a MEMBAR) per tile, and the 64 KB the P buffers took
-// now deepen the K/V ring.  The key tile width `bk` is chosen per call (multiple of 16, <= 128) so that the tiles divide the
-// sequence evenly: N = 782 runs as 7 x 112 = 784 keys instead of 7 x 128 = 896 (12.5 % less MMA and MUFU work), the T5
-// cross-attention (8 keys) as one 16-key tile.  Because the soft-clamp bounds every logit to [-50, 50],
+// now deepen the K/V ring.  The key tile width `bk` is a per-call value (multiple of 16, <= 128): 128 for self attention, 16 for
+// the T5 cross-attention's 8 keys.  Because the soft-clamp bounds every logit to [-50, 50],
 // exp(sim) cannot overflow or underflow in fp32/bf16, so no running maximum and no O rescaling is needed:
 // out = (sum_j exp(sim_j) v_j) / (sum_j exp(sim_j)) is evaluated directly.  q arrives pre-scaled by 64^-0.5 and
 // RoPE-rotated, k RoPE-rotated, V transposed ([d, keys]) -- all produced by the QKV GEMM epilogue (gemm.cu) -- so
@@ -39,6 +38,7 @@ constexpr int ATT_VSTAGE = 2 * ATT_VATOM;       // two 64-key atoms per 128-key 
 constexpr int ATT_SQ = 0;                       // 2 x 16 KB  Q   [128 q, 64 d]        (double-buffered across work items)
 constexpr int ATT_SK = 2 * 16384;               // ATT_KV x 16 KB  K   [128 keys, 64 d]
 constexpr int ATT_SV = ATT_SK + ATT_KV * 16384; // ATT_KV x 20 KB  V^T 2 x [80 rows, 64 keys]
+constexpr int ATT_SONES = ATT_SV + ATT_KV * 16384;   // row-major V takes 16 KB per slot: the ones tile (2 KB) sits in the tail of the V region
 constexpr int ATT_BAR = ATT_SV + ATT_KV * ATT_VSTAGE;
 constexpr int ATT_LENS = ATT_BAR + 256;          // clamped kv length of every kv sequence of the call
 constexpr int ATT_MAXB = 1024;                  // more kv sequences than this: lengths are read from global memory instead
@@ -62,7 +62,28 @@ __device__ __forceinline__ float softclamp_exp2_arg_exact(float z, float ex_a, f
 
 // p = 2^(z * poly(z^2)) for the 32 logits of one warp-tile, packed to bf16 pairs, in packed-pair arithmetic (FFMA2 / FMUL2:
 // half the issue slots of the scalar forms).  HI selects the degree-9 series.
-template <bool HI, int NP>
+// 2^a for a pair on the FMA / ALU pipes only (no MUFU): Cody-Waite split a = n + f with the magic-number rounding, a cubic for
+// 2^f on [-0.5, 0.5] (minimax fit, relative error < 7.5e-5, far below the bf16 rounding of P) and the integer n added into the exponent field.
+// |a| <= log2(e) * clamp = 72.2, so neither the split nor the exponent add can overflow.
+__device__ __forceinline__ void exp2_pair_fma(uint64_t a, float& r0, float& r1) {
+  const uint64_t magic = f32x2_pack(12582912.0f, 12582912.0f);                    // 1.5 * 2^23
+  const uint64_t t = f32x2_add(a, magic);                                         // n sits in the low mantissa bits
+  const uint64_t f = f32x2_sub(a, f32x2_sub(t, magic));                           // a - n
+  uint64_t p = f32x2_fma(f, f32x2_pack(0.05517167f, 0.05517167f), f32x2_pack(0.24261113f, 0.24261113f));
+  p = f32x2_fma(f, p, f32x2_pack(0.69326097f, 0.69326097f));
+  p = f32x2_fma(f, p, f32x2_pack(0.99992806f, 0.99992806f));
+  float p0, p1, t0, t1;
+  f32x2_unpack(p, p0, p1);
+  f32x2_unpack(t, t0, t1);
+  r0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  r1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+
+// p = 2^(z * poly(z^2)) for the logits of one warp-tile, packed to bf16 pairs, in packed-pair arithmetic (FFMA2 / FMUL2:
+// half the issue slots of the scalar forms).  HI selects the degree-9 series.  POLY: every fourth pair takes its exponential
+// from exp2_pair_fma instead of the MUFU unit -- ex2 (16 / clk / SM) is the binding pipe of this kernel while the FMA pipe has
+// slack (tools/pipe_bench2: 277 clk per block, 256 of them MUFU; 196 without any ex2).
+template <bool HI, int NP, bool POLY>
 __device__ __forceinline__ void exp_block(const uint32_t (&v)[32], const ClampPoly& cp, uint32_t (&pk)[16]) {
   const uint64_t c0 = f32x2_pack(cp.c0, cp.c0), c1 = f32x2_pack(cp.c1, cp.c1), c2 = f32x2_pack(cp.c2, cp.c2);
   const uint64_t c3 = f32x2_pack(cp.c3, cp.c3), c4 = f32x2_pack(cp.c4, cp.c4);
@@ -79,9 +100,16 @@ __device__ __forceinline__ void exp_block(const uint32_t (&v)[32], const ClampPo
       q = f32x2_fma(w, c2, c1);
     }
     q = f32x2_fma(w, q, c0);
-    float a0, a1;
-    f32x2_unpack(f32x2_mul(z, q), a0, a1);
-    pk[i] = pack_bf16(ex2_approx(a0), ex2_approx(a1));
+    const uint64_t a = f32x2_mul(z, q);
+    if (POLY && (i & 3) == 3) {
+      float r0, r1;
+      exp2_pair_fma(a, r0, r1);
+      pk[i] = pack_bf16(r0, r1);
+    } else {
+      float a0, a1;
+      f32x2_unpack(a, a0, a1);
+      pk[i] = pack_bf16(ex2_approx(a0), ex2_approx(a1));
+    }
   }
 }
 
@@ -172,7 +200,11 @@ __device__ __forceinline__ void walk_next_tile(ItemWalk& w, const e2b_attn_desc&
   if (++w.c.j == w.c.nt) walk_next_item(w, d, qtiles, total);
 }
 
+// VMN: V arrives as plain rows [keys, 64 d] (like K) and is the MN-major B operand of the P V product; the row sums then come
+// from a second, 16-wide MMA against a constant tile of ones.  !VMN: V^T [64 d, keys] (K-major B) whose atoms carry a ones row.
+template <bool VMN, bool POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_constant__ AttnArgs args) {
+  constexpr int VSTAGE = VMN ? 16384 : ATT_VSTAGE;          // bytes of V per ring slot
   // Used directly (no integer round-trip) so the compiler keeps the shared address space; SWIZZLE_128B needs a 1024-byte
   // aligned base: with no static shared memory the dynamic window starts at offset 0 -- checked once below.
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -235,14 +267,23 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       lens_s = nullptr;
     }
   }
-  // rows 64..79 of every V^T atom: row 64 = 1.0 (so column 64 of O accumulates the row sums of the bf16 P the MMA actually
-  // used), rows 65..79 = 0.  A whole 128-byte row is constant, so the 128-byte swizzle does not matter.  TMA only ever
-  // rewrites rows 0..63.
-  for (int i = threadIdx.x; i < ATT_KV * 2 * 16 * 8; i += ATT_THREADS) {
-    const int atom = i / 128, rem = i % 128, row = rem / 8, chunk = rem % 8;
-    const uint32_t one2 = 0x3F803F80u;   // two bf16 1.0
-    const uint32_t val = row == 0 ? one2 : 0u;
-    *reinterpret_cast<uint4*>(smem + ATT_SV + atom * ATT_VATOM + (64 + row) * 128 + chunk * 16) = make_uint4(val, val, val, val);
+  if constexpr (VMN) {
+    // a K-major [16 x 16] tile of ones (16 rows of 128 B, all 1.0): P times it puts the row sums of the bf16 P the MMA actually
+    // used into 16 extra accumulator columns (64..79 of O)
+    for (int i = threadIdx.x; i < 2048 / 16; i += ATT_THREADS) {
+      const uint32_t one2 = 0x3F803F80u;   // two bf16 1.0
+      *reinterpret_cast<uint4*>(smem + ATT_SONES + i * 16) = make_uint4(one2, one2, one2, one2);
+    }
+  } else {
+    // rows 64..79 of every V^T atom: row 64 = 1.0 (so column 64 of O accumulates the row sums of the bf16 P the MMA actually
+    // used), rows 65..79 = 0.  A whole 128-byte row is constant, so the 128-byte swizzle does not matter.  TMA only ever
+    // rewrites rows 0..63.
+    for (int i = threadIdx.x; i < ATT_KV * 2 * 16 * 8; i += ATT_THREADS) {
+      const int atom = i / 128, rem = i % 128, row = rem / 8, chunk = rem % 8;
+      const uint32_t one2 = 0x3F803F80u;   // two bf16 1.0
+      const uint32_t val = row == 0 ? one2 : 0u;
+      *reinterpret_cast<uint4*>(smem + ATT_SV + atom * ATT_VATOM + (64 + row) * 128 + chunk * 16) = make_uint4(val, val, val, val);
+    }
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -264,13 +305,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     walk_init(wpf, d, qtiles, total, lens_s, bk);
     ItemCursor& c = wc.c;
     ItemCursor& pf = wpf.c;
-    const uint32_t kv_bytes = (uint32_t)bk * 128u + (two_atoms ? 16384u : 8192u);
+    const uint32_t kv_bytes = VMN ? (uint32_t)bk * 256u : (uint32_t)bk * 128u + (two_atoms ? 16384u : 8192u);
     auto prefetch_tile = [&](const ItemCursor& t) {
       if (t.j == 0) tma_prefetch_l2_2d(&args.tmQ, d.q_col0 + t.h * ATT_D, t.b * d.q_rows_per_batch + t.qt * ATT_BQ);
       tma_prefetch_l2_2d(&args.tmK, d.k_col0 + t.h * ATT_D, t.kvb * d.kv_rows_per_batch + t.j * bk);
-      const int vr = (t.kvb * d.heads + t.h) * ATT_D;
-      tma_prefetch_l2_2d(&args.tmV, t.j * bk, vr);
-      if (two_atoms) tma_prefetch_l2_2d(&args.tmV, t.j * bk + 64, vr);
+      if constexpr (VMN) {
+        tma_prefetch_l2_2d(&args.tmV, d.v_col0 + t.h * ATT_D, t.kvb * d.kv_rows_per_batch + t.j * bk);
+      } else {
+        const int vr = (t.kvb * d.heads + t.h) * ATT_D;
+        tma_prefetch_l2_2d(&args.tmV, t.j * bk, vr);
+        if (two_atoms) tma_prefetch_l2_2d(&args.tmV, t.j * bk + 64, vr);
+      }
     };
     for (int i = 0; i < ATT_PF + ATT_KV && pf.valid; ++i) {
       if (elect_one()) prefetch_tile(pf);
@@ -293,8 +338,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         if (elect_one()) {
           mbar_arrive_expect_tx(&kv_full[s], kv_bytes);
           tma_load_2d(smem + ATT_SK + s * 16384, &args.tmK, &kv_full[s], d.k_col0 + c.h * ATT_D, c.kvb * d.kv_rows_per_batch + j * bk);
-          tma_load_2d(smem + ATT_SV + s * ATT_VSTAGE, &args.tmV, &kv_full[s], j * bk, vrow);
-          if (two_atoms) tma_load_2d(smem + ATT_SV + s * ATT_VSTAGE + ATT_VATOM, &args.tmV, &kv_full[s], j * bk + 64, vrow);
+          if constexpr (VMN) {
+            tma_load_2d(smem + ATT_SV + s * VSTAGE, &args.tmV, &kv_full[s], d.v_col0 + c.h * ATT_D, c.kvb * d.kv_rows_per_batch + j * bk);
+          } else {
+            tma_load_2d(smem + ATT_SV + s * VSTAGE, &args.tmV, &kv_full[s], j * bk, vrow);
+            if (two_atoms) tma_load_2d(smem + ATT_SV + s * VSTAGE + ATT_VATOM, &args.tmV, &kv_full[s], j * bk + 64, vrow);
+          }
           if (pf.valid) prefetch_tile(pf);
         }
         __syncwarp();
@@ -334,7 +383,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     }
   } else if (warp == ATT_W_ALLOC) {
     // ------------------------------------------------------------ O += P V issuer (A = P from TMEM, B = V^T from shared memory)
-    constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, ATT_ON);
+    constexpr uint32_t idesc_o = VMN ? umma_idesc_bf16_bmn(ATT_BQ, ATT_D) : umma_idesc_bf16(ATT_BQ, ATT_ON);
+    constexpr uint32_t idesc_1 = umma_idesc_bf16(ATT_BQ, 16);          // VMN: P x ones -> row sums
     const int ksteps = bk / 16;
     ItemWalk wp;
     walk_init(wp, d, qtiles, total, lens_s, bk);
@@ -348,13 +398,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         dbg_stamp(gp, 2);
         const uint32_t tmem_o = tmem_base + ATT_TMEM_O + ob * ATT_ON;
         const uint32_t tmem_p = tmem_base + pb * ATT_BK;
-        const uint64_t dv0 = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SV + ks * ATT_VSTAGE));
+        const uint64_t dv0 = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SV + ks * VSTAGE));   // (same encoding for the MN-major tile)
+        const uint64_t d1 = umma_desc_kmajor_sw128(smem_u32(smem + ATT_SONES));
         for (int kk = 0; kk < ksteps; ++kk) {
           // P: keys 16kk..16kk+15 are 8 TMEM columns inside the 16 the owning softmax warp wrote: 32 (kk / 2) + 8 (kk % 2)
-          // V^T: atom (kk >> 2) is +10 KB (encoded >> 4), then 32 B per 16-key step inside the swizzle atom
           const uint32_t ta = tmem_p + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8);
-          const uint64_t dv = dv0 + (uint64_t)((kk >> 2) * (ATT_VATOM >> 4) + (kk & 3) * UMMA_K_STEP_ENC);
-          umma_bf16_ts(tmem_o, ta, dv, idesc_o, (cp.j | kk) != 0 ? 1u : 0u);
+          const uint32_t acc = (cp.j | kk) != 0 ? 1u : 0u;
+          if constexpr (VMN) {
+            // V rows [keys, 64 d], 128 B per key, SWIZZLE_128B: 16 keys of a K-step are two 8-row groups, +2 KB per step
+            umma_bf16_ts(tmem_o, ta, dv0 + (uint64_t)(kk * (2048 >> 4)), idesc_o, acc);
+            umma_bf16_ts(tmem_o + ATT_D, ta, d1, idesc_1, acc);
+          } else {
+            // V^T: atom (kk >> 2) is +10 KB (encoded >> 4), then 32 B per 16-key step inside the swizzle atom
+            const uint64_t dv = dv0 + (uint64_t)((kk >> 2) * (ATT_VATOM >> 4) + (kk & 3) * UMMA_K_STEP_ENC);
+            umma_bf16_ts(tmem_o, ta, dv, idesc_o, acc);
+          }
         }
         umma_commit(&kv_empty[ks]);      // S(g) finished long before P(g) existed, so this also covers K of the slot
         umma_commit(&p_empty[pb]);
@@ -452,9 +510,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             const bool hi = !lo && !__any_sync(0xffffffffu, wm * wm >= cp.wmax);
             if (ncol > 16) {
               if (lo) {
-                exp_block<false, 16>(v, cp, pk);        // |z/clamp| <= 0.16: degree-5 series exact to 1e-5 in the exponent
+                exp_block<false, 16, POLY>(v, cp, pk);        // |z/clamp| <= 0.16: degree-5 series exact to 1e-5 in the exponent
               } else if (hi) {
-                exp_block<true, 16>(v, cp, pk);
+                exp_block<true, 16, POLY>(v, cp, pk);
               } else {                                  // rare: logits beyond the series' range -> exact tanh for the block
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
@@ -465,9 +523,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
 #pragma unroll
               for (int i = 8; i < 16; ++i) pk[i] = 0u;
               if (lo) {
-                exp_block<false, 8>(v, cp, pk);
+                exp_block<false, 8, POLY>(v, cp, pk);
               } else if (hi) {
-                exp_block<true, 8>(v, cp, pk);
+                exp_block<true, 8, POLY>(v, cp, pk);
               } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -527,6 +585,8 @@ extern "C" int e2b_attention_set_debug(long long* dev_buf) {
 extern "C" { int e2b_attention_force_bk = 0; }
 // 0: this kernel; 1: the round-1 kernel (attention_v1.cu).  Initialised from the environment (E2B_ATTN=v1) on first use.
 extern "C" { int e2b_attention_impl = -1; }
+// != 0: a quarter of the exponentials of every softmax block are evaluated on the FMA pipe (E2B_ATTN_POLY=0 switches it off)
+extern "C" { int e2b_attention_poly = 1; }
 extern "C" int e2b_attention_v1_launch(const e2b_attn_desc* d, cudaStream_t stream);
 
 extern "C" int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream) {
@@ -535,8 +595,13 @@ extern "C" int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream)
     e2b_attention_impl = (e && (e[0] == 'v' ? e[1] == '1' : e[0] == '1')) ? 1 : 0;
     const char* f = getenv("E2B_ATTN_BK");
     if (f && atoi(f) > 0) e2b_attention_force_bk = atoi(f);
+    const char* p = getenv("E2B_ATTN_POLY");
+    if (p) e2b_attention_poly = atoi(p);
   }
-  if (e2b_attention_impl == 1) return e2b_attention_v1_launch(d, stream);
+  if (e2b_attention_impl == 1) {
+    if (d->v_rowmajor) { e2b_set_kernel_error("attention: the round-1 kernel takes V^T only"); return -1; }
+    return e2b_attention_v1_launch(d, stream);
+  }
   if (d->batch <= 0 || d->heads <= 0 || d->q_rows_per_batch <= 0) return 0;
   if (d->kv_rows_per_batch <= 0) { e2b_set_kernel_error("attention: kv_rows_per_batch must be positive"); return -1; }
   if ((d->ldo % 8) || (reinterpret_cast<uintptr_t>(d->out) & 15)) { e2b_set_kernel_error("attention: out must be 16-byte aligned"); return -1; }
@@ -561,20 +626,28 @@ extern "C" int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream)
   const uint64_t k_rows = (uint64_t)kv_batches * d->kv_rows_per_batch;
   if (make_tmap_bf16(&a.tmQ, d->q, q_rows, (uint64_t)d->q_col0 + d->heads * 64, d->ldq, ATT_BQ)) return -1;
   {
-    // key tile width: the smallest multiple of 16 that covers the sequence in the same number of tiles as 128-wide ones
-    const int tiles = (d->kv_rows_per_batch + ATT_BK - 1) / ATT_BK;
-    const int per = (d->kv_rows_per_batch + tiles - 1) / tiles;
-    a.bk = (per + 15) / 16 * 16;
-    if (a.bk > ATT_BK) a.bk = ATT_BK;
+    // Key tile width.  Sequences longer than one tile use the full 128: an even split (782 keys as 7 x 112 instead of 6 x 128 + 14)
+    // measured 8 % SLOWER with both V layouts (tools/bench_attention.py) -- the softmax warps already skip the dead columns of a
+    // ragged last tile, so an even split saves no MUFU work, and it turns one nearly free tile into a seventh full-latency one.
+    // Short key sets (the T5 cross-attention: 8 keys) take the smallest multiple of 16 that holds them.
+    a.bk = d->kv_rows_per_batch >= ATT_BK ? ATT_BK : (d->kv_rows_per_batch + 15) / 16 * 16;
     if (e2b_attention_force_bk > 0) a.bk = e2b_attention_force_bk;
     if (a.bk < 16 || a.bk > ATT_BK || a.bk % 16) { e2b_set_kernel_error("attention: key tile width %d must be a multiple of 16 in [16,128]", a.bk); return -1; }
   }
   if (make_tmap_bf16(&a.tmK, d->k, k_rows, (uint64_t)d->k_col0 + d->heads * 64, d->ldk, (uint32_t)a.bk)) return -1;
-  if (make_tmap_bf16(&a.tmV, d->vt, (uint64_t)kv_batches * d->heads * 64, d->kv_rows_per_batch, d->vt_ld, 64)) return -1;
+  const bool vmn = d->v_rowmajor != 0;
+  if (vmn) {
+    if (make_tmap_bf16(&a.tmV, d->vt, k_rows, (uint64_t)d->v_col0 + d->heads * 64, d->vt_ld, (uint32_t)a.bk)) return -1;
+  } else {
+    if (make_tmap_bf16(&a.tmV, d->vt, (uint64_t)kv_batches * d->heads * 64, d->kv_rows_per_batch, d->vt_ld, 64)) return -1;
+  }
   static bool configured[E2B_MAX_DEVICES] = {false};
   bool& conf = configured[e2b_device_slot()];
   if (!conf) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
     if (e != cudaSuccess) { e2b_set_kernel_error("attention smem attribute: %s", cudaGetErrorString(e)); return -1; }
     conf = true;
   }
@@ -584,7 +657,11 @@ extern "C" int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream)
   ProfScope ps(stream, "attention", (long long)d->batch * d->q_rows_per_batch, d->kv_rows_per_batch, d->heads,
                4.0 * d->batch * d->heads * (double)d->q_rows_per_batch * d->kv_rows_per_batch * 64.0,
                2.0 * d->batch * d->heads * 64.0 * (2.0 * d->q_rows_per_batch + 2.0 * d->kv_rows_per_batch));
-  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(a);
+  const bool poly = e2b_attention_poly != 0;
+  if (vmn && poly) attention_kernel<true, true><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(a);
+  else if (vmn) attention_kernel<true, false><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(a);
+  else if (poly) attention_kernel<false, true><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(a);
+  else attention_kernel<false, false><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { e2b_set_kernel_error("attention launch: %s", cudaGetErrorString(e)); return -1; }
   return 0;

@@ -70,6 +70,8 @@ struct e2b_handle {
 
   // prepared shape
   bool f32 = false;                // error-compensated mode: bf16 A operands are (hi, lo) pairs, weights [W_hi|W_hi|W_lo]
+  bool v_rows = true;              // bf16 mode: V kept as plain rows [M, H*64] (MN-major operand of P V); false: transposed copy V^T
+                                   // (the round-1 layout: E2B_ATTN=v1 or E2B_VT=1)
   int B = 0, n = 0, nc = 0, P = 0, Pctx = 0, N = 0, Bt = 0, Npad = 0, ncpad = 0;
   size_t M = 0;
   bool conditions_set = false;
@@ -357,7 +359,7 @@ int attention_block(e2b_handle* h, int C, int heads, const bf16* w_q, const floa
   d.hgate = h->hg; d.hgate_ld = heads; d.hgate_bias = hg_b;
   if (!h->f32) {
     d.out = h->qk;
-    d.vt = h->vt; d.vt_ld = h->Npad; d.heads_v = heads;
+    d.vt = h->vt; d.vt_ld = h->v_rows ? HDs : h->Npad; d.heads_v = heads; d.v_rowmajor = h->v_rows;
   } else {
     d.out = h->qkf; d.qk_f32 = h->qkf; d.v_f32 = h->vf; d.v_f32_ld = HDs; d.heads_v = heads;
   }
@@ -370,14 +372,15 @@ int attention_block(e2b_handle* h, int C, int heads, const bf16* w_q, const floa
     if (cross) {
       a.kv_rows_per_batch = h->nc;
       a.k = h->k2[layer_ctx]; a.ldk = HDs; a.k_col0 = 0;
-      a.vt = h->vt2[layer_ctx]; a.vt_ld = h->ncpad;
+      a.vt = h->vt2[layer_ctx]; a.vt_ld = h->v_rows ? HDs : h->ncpad;
       a.kv_batch_mod = h->B; a.kv_lens = h->ctx_lens_dev;
     } else {
       a.kv_rows_per_batch = h->N;
       a.k = h->qk; a.ldk = qcols; a.k_col0 = HDs;
-      a.vt = h->vt; a.vt_ld = h->Npad;
+      a.vt = h->vt; a.vt_ld = h->v_rows ? HDs : h->Npad;
       a.kv_lens = h->lens_dev;
     }
+    a.v_rowmajor = h->v_rows; a.v_col0 = 0;
     a.hgate = h->hg; a.hgate_ld = heads;
     a.out = h->ob; a.ldo = HDs;
     a.softclamp = 50.0f;
@@ -576,7 +579,7 @@ int set_ctx(e2b_handle* h, const float* ctx_dev, const int* ctx_lens_host, cudaS
     d.heads_v = c.heads;
     if (!h->f32) {
       d.out = h->k2[l];
-      d.vt = h->vt2[l]; d.vt_ld = h->ncpad;
+      d.vt = h->vt2[l]; d.vt_ld = h->v_rows ? h->HD : h->ncpad; d.v_rowmajor = h->v_rows;
     } else {
       d.out = h->k2f[l]; d.qk_f32 = h->k2f[l]; d.v_f32 = h->v2f[l]; d.v_f32_ld = h->HD;
     }
@@ -621,6 +624,11 @@ extern "C" int e2b_create(const e2b_config* cfg, e2b_handle** out) {
   h->inner = cfg->dim * cfg->ff_mult; h->inner_t = cfg->dim_text * cfg->ff_mult; h->inner_f = cfg->dim_frames * cfg->ff_mult;
   h->nmat = cfg->depth * 6;
   h->f32 = cfg->precision == 1;
+  {
+    const char *a = getenv("E2B_ATTN"), *v = getenv("E2B_VT");
+    const bool v1 = a && (a[0] == 'v' ? a[1] == '1' : a[0] == '1');
+    h->v_rows = !(v1 || (v && v[0] == '1'));
+  }
   *out = h;
   return 0;
 }

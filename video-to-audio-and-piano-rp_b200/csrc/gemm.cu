@@ -26,6 +26,8 @@ constexpr int BK = 64;
 struct GemmArgs {
   CUtensorMap tmA[E2B_MAX_SRC];
   CUtensorMap tmB;
+  CUtensorMap tmBt;          // ragged last column tile: the same W with a box of tail_rows rows (no zero-filled rows through the pipe)
+  int tail_rows;             // 0: N is a multiple of the tile width (or the tail is a full box); else valid columns of the last tile, rounded up to 16
   int kb_end[E2B_MAX_SRC];
   e2b_gemm_desc d;
 };
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
   if (warp == W_TMA && lane == 0) {
     for (int s = 0; s < d.num_src; ++s) tma_prefetch_desc(&args.tmA[s]);
     tma_prefetch_desc(&args.tmB);
+    if (args.tail_rows > 0) tma_prefetch_desc(&args.tmBt);
   }
   if (warp == W_MMA && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -185,15 +188,19 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      const int n_tile = tile % n_tiles;
+      const int m0 = (tile / n_tiles) * BM, n0 = n_tile * BN;
+      const bool tail = args.tail_rows > 0 && n_tile == n_tiles - 1;
+      const CUtensorMap* tmb = tail ? &args.tmBt : &args.tmB;
+      const uint32_t bytes = tail ? (uint32_t)(Cfg::A_BYTES + args.tail_rows * BK * 2) : (uint32_t)Cfg::STAGE_BYTES;
       int src = 0, kb0 = 0;
       for (int kb = 0; kb < KB; ++kb) {
         while (kb >= args.kb_end[src]) { kb0 = args.kb_end[src]; ++src; }
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          mbar_arrive_expect_tx(&full[stage], bytes);
           tma_load_2d(sA + stage * Cfg::A_BYTES, &args.tmA[src], &full[stage], (kb - kb0) * BK, m0);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &args.tmB, &full[stage], kb * BK, n0);
+          tma_load_2d(sB + stage * Cfg::B_BYTES, tmb, &full[stage], kb * BK, n0);
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -201,13 +208,16 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
     }
   } else if (warp == W_MMA) {
     // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      // A ragged last column tile (QKV + head-gate: N = 3088 = 12 x 256 + 16) only multiplies the columns it has, rounded up to the
+      // MMA's N granularity of 16: a 16-column tile costs 1/16 of the tensor time instead of a full tile (8 % of the QKV GEMMs)
+      const int nv = min(BN, d.N - (tile % n_tiles) * BN);
+      const uint32_t idesc = umma_idesc_bf16(BM, (uint32_t)((nv + 15) & ~15));
       mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN;
@@ -349,7 +359,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
-          if (col0 >= d.k_end && col0 < d.v_end && d.v_f32 == nullptr) {
+          if (col0 >= d.k_end && col0 < d.v_end && d.v_f32 == nullptr && !d.v_rowmajor) {
             // V^T store: thread = key position, so the 32 lanes of a store are 32 consecutive keys (64 contiguous bytes)
             const int row = m0 + ew * 32 + lane;
             if (row < d.M) {
@@ -379,6 +389,12 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
                 else *reinterpret_cast<uint2*>(R.out[k] + col * 2) = pack4_bf16(o);
               }
             }
+          } else if (col0 < d.v_end && d.v_f32 == nullptr) {   // v as plain bf16 rows [M, vt_ld] (MN-major operand of the attention kernel)
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (R.out[k])
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.vt) + (size_t)(m0 + ew * 32 + 4 * k + rsub) * d.vt_ld + (col - d.k_end)) =
+                    pack4_bf16(bufr[4 * k * EPI_PITCH4]);
           } else if (col0 < d.v_end) {               // fp32 mode: v as plain fp32 [M, v_f32_ld]
 #pragma unroll
             for (int k = 0; k < 8; ++k)
@@ -630,6 +646,11 @@ extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
     return -1;
   }
   if (make_tmap_bf16(&a.tmB, d->w, d->N, d->K, d->ldw, bn256 ? 256 : 128)) return -1;
+  {
+    const int bn = bn256 ? 256 : 128, rem = d->N % bn, rows16 = (rem + 15) / 16 * 16;
+    a.tail_rows = (rem > 0 && rows16 < bn) ? rows16 : 0;
+    if (a.tail_rows && make_tmap_bf16(&a.tmBt, d->w, d->N, d->K, d->ldw, (uint32_t)a.tail_rows)) return -1;
+  }
 #define E2B_DISPATCH(BN_, EW_)                                                        \
   switch (d->epi) {                                                                   \
     case E2B_EPI_BF16: return launch_t<BN_, E2B_EPI_BF16, EW_>(a, stream);            \

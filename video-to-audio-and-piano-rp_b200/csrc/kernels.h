@@ -58,6 +58,8 @@ typedef struct e2b_gemm_desc {
   float* qk_f32;
   float* v_f32;
   int v_f32_ld;
+  // EPI_QKV, bf16 mode: v_rowmajor != 0 stores v as plain rows, `vt` = bf16 [M, vt_ld] with column (packed col - k_end), instead of V^T
+  int v_rowmajor;
 } e2b_gemm_desc;
 
 int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream);
@@ -81,6 +83,10 @@ typedef struct e2b_attn_desc {
   const float* hgate; int hgate_ld;   // [rows, heads] sigmoid gate or NULL
   void* out; int ldo;
   float softclamp;           // 50.0
+  // v_rowmajor != 0: `vt` points to V as plain rows instead -- bf16 [kv rows, vt_ld] with head h at columns [v_col0 + h*64, +64),
+  // the same layout as k (no transposed copy; the P V product takes it as an MN-major operand)
+  int v_rowmajor;
+  int v_col0;
 } e2b_attn_desc;
 
 int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream);

@@ -219,6 +219,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// The same with the B operand MN-major (bit 16): B tile stored as rows of K with the N extent contiguous (64 bf16 = one
+// 128-byte swizzle row), e.g. V [keys, d] as the B operand of P V.  Canonical layout (CUTLASS make_umma_desc<Major::MN>, SW128):
+// ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units -- 8-row groups along K are SBO = 1024 B apart, a K-step of 16 rows is +2 KB.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(uint32_t M, uint32_t N) { return umma_idesc_bf16(M, N) | (1u << 16); }
+
 // ---------------------------------------------------------------- small helpers
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -239,6 +244,16 @@ __device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
 __device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
   uint64_t r;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f32x2_sub(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
 __device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {

@@ -37,7 +37,7 @@ class GemmDesc(C.Structure):
         ('rope', C.c_void_p), ('pos_off', C.c_int),
         ('vt', C.c_void_p), ('vt_ld', C.c_int), ('heads_v', C.c_int),
         ('hgate', C.c_void_p), ('hgate_ld', C.c_int), ('hgate_bias', C.c_void_p),
-        ('split', C.c_int), ('qk_f32', C.c_void_p), ('v_f32', C.c_void_p), ('v_f32_ld', C.c_int),
+        ('split', C.c_int), ('qk_f32', C.c_void_p), ('v_f32', C.c_void_p), ('v_f32_ld', C.c_int), ('v_rowmajor', C.c_int),
     ]
 
 
@@ -49,7 +49,7 @@ class AttnDesc(C.Structure):
         ('vt', C.c_void_p), ('vt_ld', C.c_int), ('kv_batch_mod', C.c_int),
         ('kv_lens', C.c_void_p), ('kv_lens_add', C.c_int),
         ('hgate', C.c_void_p), ('hgate_ld', C.c_int),
-        ('out', C.c_void_p), ('ldo', C.c_int), ('softclamp', C.c_float),
+        ('out', C.c_void_p), ('ldo', C.c_int), ('softclamp', C.c_float), ('v_rowmajor', C.c_int), ('v_col0', C.c_int),
     ]
 
 
