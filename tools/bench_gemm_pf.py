@@ -1,0 +1,72 @@
+"""A/B of the A-operand L2 prefetch cursor (e2b_gemm_prefetch_kb) on the model's GEMM shapes at the C2 row count, kernel-level
+C-ABI, CUDA events.  Between timed launches a 1 GB buffer is rewritten so that A is cold in L2, as it is inside the forward
+(the previous kernel's output is 0.2-1 GB)."""
+import ctypes as C, math, sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'video-to-audio-and-piano-rp_b200'), os.path.join(ROOT, 'tests')]
+import torch
+from e2_tts_pytorch import _lib
+from gpu_util import gemm, DEV
+M = 100096
+knob = C.c_int.in_dll(_lib.lib(), 'e2b_gemm_prefetch_kb')
+flush = torch.empty(256 * 1024 * 1024, device=DEV)
+
+
+def timeit(N, K, epi, extra, srcs):
+    a = [torch.randn(M, k, device=DEV).to(torch.bfloat16) for k in srcs]
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(torch.bfloat16)
+    gemm(M, N, K, a, w, epi, **extra)
+    tot = 0.0
+    for _ in range(4):
+        flush.fill_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        gemm(M, N, K, a, w, epi, **extra)
+        e1.record(); torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / 4 * 1e3
+
+
+def case(name, N, srcs, epi, mk):
+    K = sum(srcs)
+    row = f'{name:22s} N={N:5d} K={K:5d}:'
+    for pf in (0, 6, 12, 24):
+        knob.value = pf
+        us = timeit(N, K, epi, mk(), srcs)
+        row += f'  pf={pf:2d} {us:7.1f} us ({2 * M * N * K / us / 1e6:5.0f} TF/s)'
+    knob.value = 0
+    print(row, flush=True)
+
+
+lens = torch.full((128,), 782, device=DEV, dtype=torch.int32)
+def resid(N, b16=True):
+    out = torch.randn(M, N, device=DEV)
+    extra = dict(out=out, ldo=N, resid=out, ldr=N, gate=torch.rand(N, device=DEV), gate_bstride=0, lens=lens, rows_per_batch=782)
+    if b16:
+        extra.update(out_b16=torch.empty(M, N, device=DEV, dtype=torch.bfloat16), ldo_b16=N)
+    return lambda: extra
+def geglu(N):
+    extra = dict(out=torch.empty(M, N // 2, device=DEV, dtype=torch.bfloat16), ldo=N // 2, bias=torch.randn(N, device=DEV))
+    return lambda: extra
+def qkv(H):
+    HD = H * 64
+    extra = dict(out=torch.empty(M, 2 * HD, device=DEV, dtype=torch.bfloat16), ldo=2 * HD, q_end=HD, k_end=2 * HD, v_end=3 * HD, q_scale=0.125,
+                 rope=torch.randn(782, 32, 2, device=DEV), pos_off=0, rows_per_batch=782, vt=torch.zeros(M, HD, device=DEV, dtype=torch.bfloat16), vt_ld=HD,
+                 heads_v=H, hgate=torch.empty(M, H, device=DEV), hgate_ld=H, hgate_bias=torch.zeros(H, device=DEV), v_rowmajor=1)
+    return lambda: extra
+
+case('geglu text', 10240, [1280], _lib.EPI_GEGLU, geglu(10240))
+case('geglu audio', 8192, [1024], _lib.EPI_GEGLU, geglu(8192))
+case('geglu frames', 4096, [512], _lib.EPI_GEGLU, geglu(4096))
+case('ff2 text', 1280, [5120], _lib.EPI_RESID, resid(1280))
+case('ff2 audio', 1024, [4096], _lib.EPI_RESID, resid(1024))
+case('ff2 frames', 512, [2048], _lib.EPI_RESID, resid(512))
+case('cross tfa', 1024, [1024, 1280, 512], _lib.EPI_RESID, resid(1024))
+case('cross at', 1280, [1024, 1280], _lib.EPI_RESID, resid(1280, False))
+case('cross af', 512, [1024, 512], _lib.EPI_RESID, resid(512, False))
+case('out text', 1280, [1024], _lib.EPI_RESID, resid(1280, False))
+case('out audio', 1024, [1024], _lib.EPI_RESID, resid(1024, False))
+case('out frames', 512, [512], _lib.EPI_RESID, resid(512, False))
+case('qkv text', 3088, [1280], _lib.EPI_QKV, qkv(16))
+case('qkv audio', 3088, [1024], _lib.EPI_QKV, qkv(16))
+case('qkv frames', 1544, [512], _lib.EPI_QKV, qkv(8))

@@ -585,8 +585,8 @@ extern "C" int e2b_attention_set_debug(long long* dev_buf) {
 extern "C" { int e2b_attention_force_bk = 0; }
 // 0: this kernel; 1: the round-1 kernel (attention_v1.cu).  Initialised from the environment (E2B_ATTN=v1) on first use.
 extern "C" { int e2b_attention_impl = -1; }
-// != 0: a quarter of the exponentials of every softmax block are evaluated on the FMA pipe (E2B_ATTN_POLY=0 switches it off)
-extern "C" { int e2b_attention_poly = 1; }
+// != 0: a quarter of the exponentials of every softmax block are evaluated on the FMA pipe (E2B_ATTN_POLY=1; measured slower, off)
+extern "C" { int e2b_attention_poly = 0; }
 extern "C" int e2b_attention_v1_launch(const e2b_attn_desc* d, cudaStream_t stream);
 
 extern "C" int e2b_attention_launch(const e2b_attn_desc* d, cudaStream_t stream) {

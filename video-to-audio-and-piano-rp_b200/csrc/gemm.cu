@@ -12,6 +12,7 @@
 //     transposed V store for the attention kernel, sigmoid value-head gate).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -28,6 +29,7 @@ struct GemmArgs {
   CUtensorMap tmB;
   CUtensorMap tmBt;          // ragged last column tile: the same W with a box of tail_rows rows (no zero-filled rows through the pipe)
   int tail_rows;             // 0: N is a multiple of the tile width (or the tail is a full box); else valid columns of the last tile, rounded up to 16
+  int pf_kb;                 // A-operand L2 prefetch distance in 64-wide K blocks (0 = off)
   int kb_end[E2B_MAX_SRC];
   e2b_gemm_desc d;
 };
@@ -187,6 +189,22 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
+    // Optional A-operand prefetch cursor (OFF by default, E2B_GEMM_PF=<K blocks> to try it): the CTA that owns column tile 0 of a
+    // row block asks the TMA unit to pull the A block into L2 pf_kb K blocks ahead of its own loads.  The idea was that A (0.2-1 GB,
+    // written by the previous kernel) is cold in L2 with only STAGES - 1 K blocks in flight.  MEASURED: a clear loss on every shape
+    // (tools/bench_gemm_pf.py, profiles/r02_gemm_prefetch_ab.txt: GEGLU text 1385 -> 1197 TF/s, FF2 audio 1125 -> 950, out-projections
+    // unchanged) and 1.6-1.9x the algorithmic DRAM reads under ncu -- the operand ring already covers the latency, the extra requests
+    // only compete with the real loads.  Kept as a switch so the result can be reproduced.
+    int pf_tile = blockIdx.x, pf_k = 0, pf_src = 0, pf_k0 = 0;
+    auto pf_step = [&]() {
+      if (pf_tile >= total) return;
+      if (pf_tile % n_tiles == 0 && elect_one())
+        tma_prefetch_l2_2d(&args.tmA[pf_src], (pf_k - pf_k0) * BK, (pf_tile / n_tiles) * BM);
+      if (++pf_k == KB) { pf_k = 0; pf_src = 0; pf_k0 = 0; pf_tile += gridDim.x; }
+      else while (pf_k >= args.kb_end[pf_src]) { pf_k0 = args.kb_end[pf_src]; ++pf_src; }
+    };
+    if (args.pf_kb > 0)
+      for (int i = 0; i < args.pf_kb; ++i) pf_step();
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       const int n_tile = tile % n_tiles;
       const int m0 = (tile / n_tiles) * BM, n0 = n_tile * BN;
@@ -203,6 +221,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
           tma_load_2d(sB + stage * Cfg::B_BYTES, tmb, &full[stage], kb * BK, n0);
         }
         __syncwarp();
+        if (args.pf_kb > 0) pf_step();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -608,6 +627,8 @@ extern "C" void e2b_set_kernel_error(const char* fmt, ...) {
 extern "C" const char* e2b_kernel_last_error(void) { return g_err; }
 
 // K threshold (inclusive) below which the 8-epilogue-warp configuration is used; settable for tuning / A-B tests.
+// A-operand L2 prefetch distance in K blocks of 64 (0 = off); settable for A/B tests (E2B_GEMM_PF)
+extern "C" int e2b_gemm_prefetch_kb = -1;
 extern "C" int e2b_gemm_ew8_max_k = 1536;   // tools/bench_gemm3.py: 8 warps win up to K=1280, tie at 2048, lose at 5120
 
 extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
@@ -645,6 +666,11 @@ extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
     e2b_set_kernel_error("gemm: QKV segment ends must be multiples of 64 and rows_per_batch > 0");
     return -1;
   }
+  if (e2b_gemm_prefetch_kb < 0) {
+    const char* e = getenv("E2B_GEMM_PF");
+    e2b_gemm_prefetch_kb = e ? atoi(e) : 0;
+  }
+  a.pf_kb = e2b_gemm_prefetch_kb;
   if (make_tmap_bf16(&a.tmB, d->w, d->N, d->K, d->ldw, bn256 ? 256 : 128)) return -1;
   {
     const int bn = bn256 ? 256 : 128, rem = d->N % bn, rows16 = (rem + 15) / 16 * 16;

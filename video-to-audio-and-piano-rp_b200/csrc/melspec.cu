@@ -16,31 +16,48 @@ namespace e2b {
 constexpr int MEL_THREADS = 256;
 constexpr int MEL_FR = 8;        // frames per CTA (one 32-byte output segment per mel row)
 
+// First / one-past-last frequency bin with a non-zero weight, per mel filter (triangular filters touch 3-45 of the 513 bins:
+// the dense [bins x mels] product of the first version spent most of its FMAs on zeros).  One thread per filter, run once per call.
+__global__ void mel_ranges_kernel(const float* __restrict__ fb, int nbins, int n_mels, int2* __restrict__ range) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_mels) return;
+  int lo = nbins, hi = 0;
+  for (int k = 0; k < nbins; ++k)
+    if (fb[(size_t)k * n_mels + m] != 0.f) { lo = min(lo, k); hi = k + 1; }
+  range[m] = make_int2(lo, hi > lo ? hi : lo);
+}
+
+// Two real frames share one complex FFT: z = x1 + i x2 (windowed), Z = FFT(z), and by conjugate symmetry
+//   X1[k] = (Z[k] + conj(Z[N-k])) / 2 ,  X2[k] = (Z[k] - conj(Z[N-k])) / (2i)   ->  |X1|, |X2| for k = 0..N/2.
 __global__ void __launch_bounds__(MEL_THREADS) melspec_kernel(const float* __restrict__ wav, int nw, int n_fft, int log2n, int hop,
                                                               int n_mels, int T, const float* __restrict__ window,
                                                               const float* __restrict__ fb, const float2* __restrict__ tw,
-                                                              float* __restrict__ out, float log_eps) {
+                                                              const int2* __restrict__ range, float* __restrict__ out, float log_eps) {
   extern __shared__ float sm[];
   float2* z = reinterpret_cast<float2*>(sm);          // n_fft complex
-  float* mag = sm + 2 * n_fft;                        // n_fft/2 + 1
-  float* tile = mag + (n_fft / 2 + 1);                // n_mels * MEL_FR
-  float* part = tile + n_mels * MEL_FR;               // MEL_THREADS partial sums
+  float* mag = sm + 2 * n_fft;                        // 2 x (n_fft/2 + 1): the two frames of a pair
+  const int nbins = n_fft / 2 + 1;
+  float* tile = mag + 2 * nbins;                      // n_mels * MEL_FR
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * MEL_FR;
   const float* x = wav + (size_t)b * nw;
-  const int nbins = n_fft / 2 + 1;
   const int half = n_fft / 2;
 
-  for (int fr = 0; fr < MEL_FR; ++fr) {
+  for (int fr = 0; fr < MEL_FR; fr += 2) {
     const int t = t0 + fr;
     if (t >= T) break;      // uniform
+    const bool two = t + 1 < T;
     const int start = t * hop - half;
     for (int i = threadIdx.x; i < n_fft; i += MEL_THREADS) {
-      int s = start + i;
-      if (s < 0) s = -s;
-      if (s >= nw) s = 2 * (nw - 1) - s;
+      int s1 = start + i;
+      if (s1 < 0) s1 = -s1;
+      if (s1 >= nw) s1 = 2 * (nw - 1) - s1;
+      int s2 = start + hop + i;
+      if (s2 < 0) s2 = -s2;
+      if (s2 >= nw) s2 = 2 * (nw - 1) - s2;
+      const float w = window[i];
       const int r = __brev((unsigned)i) >> (32 - log2n);
-      z[r] = make_float2(x[s] * window[i], 0.f);
+      z[r] = make_float2(x[s1] * w, two ? x[s2] * w : 0.f);
     }
     __syncthreads();
     for (int st = 0; st < log2n; ++st) {
@@ -56,28 +73,26 @@ __global__ void __launch_bounds__(MEL_THREADS) melspec_kernel(const float* __res
       }
       __syncthreads();
     }
-    for (int k = threadIdx.x; k < nbins; k += MEL_THREADS) mag[k] = sqrtf(z[k].x * z[k].x + z[k].y * z[k].y);
-    __syncthreads();
-    // filterbank: split the bins over `ways` thread groups per mel
-    const int ways = MEL_THREADS / n_mels > 0 ? MEL_THREADS / n_mels : 1;
-    for (int m0 = 0; m0 < n_mels; m0 += MEL_THREADS) {
-      const int m = m0 + (threadIdx.x % (n_mels < MEL_THREADS ? n_mels : MEL_THREADS));
-      const int way = threadIdx.x / (n_mels < MEL_THREADS ? n_mels : MEL_THREADS);
-      float acc = 0.f;
-      if (m < n_mels && way < ways) {
-        const int per = (nbins + ways - 1) / ways;
-        const int k0 = way * per, k1 = min(nbins, k0 + per);
-        for (int k = k0; k < k1; ++k) acc = fmaf(mag[k], __ldg(fb + (size_t)k * n_mels + m), acc);
-      }
-      part[threadIdx.x] = acc;
-      __syncthreads();
-      if (m < n_mels && way == 0) {
-        float s = 0.f;
-        for (int wy = 0; wy < ways; ++wy) s += part[wy * (n_mels < MEL_THREADS ? n_mels : MEL_THREADS) + (m - m0)];
-        tile[m * MEL_FR + fr] = logf(fmaxf(s, log_eps));
-      }
-      __syncthreads();
+    for (int k = threadIdx.x; k < nbins; k += MEL_THREADS) {
+      const float2 p = z[k], q = z[(n_fft - k) & (n_fft - 1)];
+      const float ar = p.x + q.x, ai = p.y - q.y;     // Z[k] + conj(Z[N-k]) = 2 X1[k]
+      const float br = p.x - q.x, bi = p.y + q.y;     // Z[k] - conj(Z[N-k]) = 2i X2[k]
+      mag[k] = 0.5f * sqrtf(ar * ar + ai * ai);
+      mag[nbins + k] = 0.5f * sqrtf(br * br + bi * bi);
     }
+    __syncthreads();
+    // filterbank over the non-zero bins of every filter: thread = (frame of the pair, mel)
+    for (int i = threadIdx.x; i < 2 * n_mels; i += MEL_THREADS) {
+      const int which = i / n_mels, m = i - which * n_mels;
+      if (which == 0 || two) {
+        const int2 rg = range[m];
+        const float* mg = mag + which * nbins;
+        float acc = 0.f;
+        for (int k = rg.x; k < rg.y; ++k) acc = fmaf(mg[k], __ldg(fb + (size_t)k * n_mels + m), acc);
+        tile[m * MEL_FR + fr + which] = logf(fmaxf(acc, log_eps));
+      }
+    }
+    __syncthreads();
   }
   const int nfr = min(MEL_FR, T - t0);
   for (int i = threadIdx.x; i < n_mels * MEL_FR; i += MEL_THREADS) {
@@ -86,11 +101,18 @@ __global__ void __launch_bounds__(MEL_THREADS) melspec_kernel(const float* __res
   }
 }
 
-static std::map<int, float2*> g_twiddles;
+// per-device tables: twiddles per n_fft, and a scratch array for the filter ranges (rewritten by every call, on the call's stream)
+struct MelTables {
+  std::map<int, float2*> twiddles;
+  int2* ranges = nullptr;
+  int ranges_cap = 0;
+};
+static MelTables g_mel[E2B_MAX_DEVICES];
 
 static float2* twiddles_for(int n_fft) {
-  auto it = g_twiddles.find(n_fft);
-  if (it != g_twiddles.end()) return it->second;
+  MelTables& tb = g_mel[e2b_device_slot()];
+  auto it = tb.twiddles.find(n_fft);
+  if (it != tb.twiddles.end()) return it->second;
   std::vector<float2> h(n_fft / 2);
   for (int k = 0; k < n_fft / 2; ++k) {
     const double a = -2.0 * M_PI * (double)k / (double)n_fft;
@@ -99,8 +121,20 @@ static float2* twiddles_for(int n_fft) {
   float2* d = nullptr;
   if (cudaMalloc(&d, h.size() * sizeof(float2)) != cudaSuccess) return nullptr;
   if (cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
-  g_twiddles[n_fft] = d;
+  tb.twiddles[n_fft] = d;
   return d;
+}
+
+static int2* ranges_for(int n_mels) {
+  MelTables& tb = g_mel[e2b_device_slot()];
+  if (tb.ranges_cap < n_mels) {
+    if (tb.ranges) cudaFree(tb.ranges);
+    tb.ranges = nullptr;
+    tb.ranges_cap = 0;
+    if (cudaMalloc(&tb.ranges, sizeof(int2) * (size_t)n_mels) != cudaSuccess) return nullptr;
+    tb.ranges_cap = n_mels;
+  }
+  return tb.ranges;
 }
 
 }  // namespace e2b
@@ -115,7 +149,10 @@ extern "C" int e2b_melspec_launch(const float* wav, int B, int nw, int n_fft, in
   if (nw <= n_fft / 2) { e2b_set_kernel_error("melspec: waveform shorter than the reflect padding"); return -1; }
   if (n_mels <= 0 || B <= 0 || hop <= 0) { e2b_set_kernel_error("melspec: bad arguments"); return -1; }
   const int T = nw / hop + 1;
-  const size_t smem = (2 * n_fft + n_fft / 2 + 1 + n_mels * MEL_FR + MEL_THREADS) * sizeof(float);
+  const size_t smem = (2 * n_fft + 2 * (n_fft / 2 + 1) + n_mels * MEL_FR) * sizeof(float);
+  int2* range = ranges_for(n_mels);
+  if (!range) { e2b_set_kernel_error("melspec: filter range table allocation failed"); return -1; }
+  mel_ranges_kernel<<<(n_mels + 127) / 128, 128, 0, stream>>>(fb, n_fft / 2 + 1, n_mels, range);
   static size_t configured_bytes[E2B_MAX_DEVICES] = {0};
   size_t& configured = configured_bytes[e2b_device_slot()];
   if (smem > 48 * 1024 && smem > configured) {
@@ -128,7 +165,7 @@ extern "C" int e2b_melspec_launch(const float* wav, int B, int nw, int n_fft, in
   dim3 grid((T + MEL_FR - 1) / MEL_FR, B);
   ProfScope ps(stream, "melspec", B, nw, n_mels, 0.0, 4.0 * B * ((double)nw + (double)n_mels * T));
   melspec_kernel<<<grid, MEL_THREADS, smem, stream>>>(wav, nw, n_fft, log2n, hop, n_mels, T, window, fb,
-                                                      reinterpret_cast<const float2*>(twiddle), out, log_eps);
+                                                      reinterpret_cast<const float2*>(twiddle), range, out, log_eps);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { e2b_set_kernel_error("melspec launch: %s", cudaGetErrorString(e)); return -1; }
   return 0;
