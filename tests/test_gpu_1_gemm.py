@@ -1,4 +1,5 @@
 """tcgen05 GEMM (csrc/gemm.cu) against torch on the same bf16 operands."""
+import ctypes
 import math
 
 import pytest
@@ -91,6 +92,60 @@ def test_geglu_epilogue():
     assert rel(out, ref) < 5e-3
 
 
+@pytest.mark.parametrize('dim', [128, 1280])          # 8 epilogue warps (K <= 1536) in both; one and several K blocks
+def test_geglu_and_qkv_row_scale(dim):
+    """Norm as a row scale, consuming side: accumulator rows times sqrt(C) / max(||x||, 1e-12) with ||x||^2 given as partial sums,
+    before bias / GELU (GEGLU) and before RoPE / q scale / V / head gate (QKV) -- equal to feeding the normalised rows."""
+    M, inner, H, Nseq = 333, 512, 2, 111
+    g = torch.Generator().manual_seed(dim)
+    x = torch.randn(M, dim, generator=g).to(DEV) * (torch.rand(M, 1, generator=g).to(DEV) * 4 + 0.1)
+    x[5] = 0                                                              # a zero row: the eps branch (scale sqrt(C) / 1e-12, result 0)
+    a = bf(x)
+    parts = 3
+    ssq = (x * x).sum(1)
+    split = torch.rand(parts, M, device=DEV)
+    ss = (split / split.sum(0, keepdim=True) * ssq[None]).contiguous()
+    rs = math.sqrt(dim) / ssq.sqrt().clamp_min(1e-12)
+    an = a.float() * rs[:, None]                                          # what an rmsnorm with unit gain would have fed
+    w = (torch.randn(2 * inner, dim, generator=g) / math.sqrt(dim)).to(DEV)
+    b = torch.randn(2 * inner, generator=g).to(DEV)
+    order = torch.cat([torch.cat([torch.arange(t * 128, t * 128 + 128), inner + torch.arange(t * 128, t * 128 + 128)])
+                       for t in range(inner // 128)]).to(DEV)
+    wp, bp = bf(w[order]).contiguous(), b[order].contiguous()
+    out = torch.zeros(M, inner, device=DEV, dtype=torch.bfloat16)
+    gemm(M, 2 * inner, dim, [a], wp, _lib.EPI_GEGLU, out=out, ldo=inner, bias=bp, in_row_ss=ss, in_row_parts=parts, in_row_ss_ld=M,
+         in_row_mult=math.sqrt(dim))
+    h = an @ bf(w).float().t() + b
+    assert rel(out, h[:, :inner] * torch.nn.functional.gelu(h[:, inner:])) < 5e-3
+
+    HD = H * 64
+    wq = bf(torch.randn(3 * HD + H, dim, generator=g) / math.sqrt(dim)).to(DEV)
+    hb = torch.randn(H, generator=g).to(DEV)
+    ang = torch.arange(Nseq).float()[:, None] * (1. / (10000 ** (torch.arange(0, 64, 2).float() / 64)))[None, :]
+    rope = torch.stack((ang.cos(), ang.sin()), -1).to(DEV).contiguous()
+    for rows in (1, 0):
+        qk = torch.zeros(M, 2 * HD, device=DEV, dtype=torch.bfloat16)
+        hg = torch.zeros(M, H, device=DEV)
+        vbuf = torch.zeros(M, HD, device=DEV, dtype=torch.bfloat16) if rows else torch.zeros(3 * H * 64, 112, device=DEV, dtype=torch.bfloat16)
+        gemm(M, 3 * HD + H, dim, [a], wq, _lib.EPI_QKV, out=qk, ldo=2 * HD, q_end=HD, k_end=2 * HD, v_end=3 * HD, q_scale=0.125, rope=rope,
+             pos_off=0, rows_per_batch=Nseq, vt=vbuf, vt_ld=HD if rows else 112, heads_v=H, hgate=hg, hgate_ld=H, hgate_bias=hb,
+             v_rowmajor=rows, in_row_ss=ss, in_row_parts=parts, in_row_ss_ld=M, in_row_mult=math.sqrt(dim))
+        full = an @ wq.float().t()
+
+        def rot(t):
+            t = t.reshape(3, Nseq, H, 32, 2)
+            c, sn = rope[None, :, None, :, 0], rope[None, :, None, :, 1]
+            return torch.stack((t[..., 0] * c - t[..., 1] * sn, t[..., 1] * c + t[..., 0] * sn), -1).reshape(M, HD)
+
+        assert rel(qk[:, :HD], rot(full[:, :HD]) * 0.125) < 5e-3 and rel(qk[:, HD:], rot(full[:, HD:2 * HD])) < 5e-3
+        v = full[:, 2 * HD:3 * HD]
+        if rows:
+            assert rel(vbuf, v) < 5e-3
+        else:
+            assert rel(vbuf[:, :Nseq], v.reshape(3, Nseq, H, 64).permute(0, 2, 3, 1).reshape(3 * H * 64, Nseq)) < 5e-3
+        assert rel(hg, torch.sigmoid(full[:, 3 * HD:] + hb)) < 1e-4
+
+
 def test_resid_gate_mask_epilogue():
     B, Nseq, K, C = 3, 70, 128, 192
     M = B * Nseq
@@ -108,6 +163,111 @@ def test_resid_gate_mask_epilogue():
     ref = resid.reshape(B, Nseq, C) + torch.where(valid, y, torch.zeros_like(y))
     assert rel(out.reshape(B, Nseq, C), ref) < 1e-5
     assert rel(outb, ref.reshape(M, C)) < 5e-3
+
+
+@pytest.mark.parametrize('tma', [1, 0], ids=['tma_epilogue', 'classic_epilogue'])
+@pytest.mark.parametrize('B,Nseq,K,C,per_batch,b16,bias_on', [
+    (30, 170, 128, 512, True, True, True),      # 2 column tiles, rows not a multiple of 128, per-batch gate rows
+    (9, 300, 1024, 1024, False, True, False),   # 8 warps / two residual tiles (K <= 3072), shared gate vector, no bias
+    (14, 150, 3200, 1280, False, True, True),   # 4 warps / one residual tile (K > 3072)
+    (24, 90, 256, 1100, False, False, True),    # ragged last column tile (1100 = 4 x 256 + 76: a chunk of 12 live columns), no bf16 copy
+    (3, 782, 512, 1056, True, True, False),     # last tile of one 32-column chunk: the second warp group has no chunk there
+    (2, 100, 256, 512, True, True, True),       # few rows: 128-wide tiles (one wave), 4 warps / one residual tile
+    (1, 77, 64, 192, False, True, False),       # narrow N, a 64-column last tile
+])
+def test_resid_epilogue_wide_tiles(B, Nseq, K, C, per_batch, b16, bias_on, tma):
+    """EPI_RESID on 256-wide tiles, both epilogues (E2B_RESID_TMA): the residual stream moved by the TMA unit in a row-per-lane
+    layout, and the classic load / transpose / store one.  In place (out aliases resid), row mask, gate, bias, bf16 copy."""
+    import ctypes as C_
+    knob = C_.c_int.in_dll(_lib.lib(), 'e2b_gemm_resid_tma')
+    M = B * Nseq
+    a, w = _ab(M, C, K, B + Nseq)
+    bias = torch.randn(C, device=DEV) if bias_on else None
+    resid = torch.randn(M, C, device=DEV)
+    gate = torch.rand(B if per_batch else 1, C, device=DEV)
+    lens = torch.tensor([Nseq - 3 * (i % 20) for i in range(B)], device=DEV, dtype=torch.int32)
+    ss = torch.full(((C + 127) // 128, M), float('nan'), device=DEV) if tma else None
+    raw = torch.full((M + 2, C), 777.0, device=DEV)                      # guard rows around the in-place stream
+    out = raw[1:M + 1]
+    out.copy_(resid)
+    outb = torch.full((M + 1, C), -5.0, device=DEV, dtype=torch.bfloat16)
+    kw = dict(out=out, ldo=C, resid=out, ldr=C, gate=gate, gate_bstride=C if per_batch else 0, lens=lens, rows_per_batch=Nseq)
+    if bias_on:
+        kw['bias'] = bias
+    if b16:
+        kw.update(out_b16=outb, ldo_b16=C)
+    if tma:
+        kw.update(row_ss=ss, row_ss_ld=M)
+    knob.value = tma
+    try:
+        gemm(M, C, K, [a], w, _lib.EPI_RESID, **kw)
+    finally:
+        knob.value = 1
+    variant = (C_.c_int * 3).in_dll(_lib.lib(), 'e2b_gemm_last_variant')
+    wide = M * ((C + 127) // 128) > 128 * 148 and (C % 256 == 0 or C > 1024)
+    assert list(variant)[:2] == [5 if tma else _lib.EPI_RESID, 256 if wide else 128], list(variant)   # the epilogue under test really ran
+    assert variant[2] == ((8 if K <= (3072 if tma else 1536) else 4) if wide else 4)
+    y = (a.float() @ w.float().t() + (bias if bias_on else 0)).reshape(B, Nseq, C) * (gate[:, None, :] if per_batch else gate[None])
+    valid = (torch.arange(Nseq, device=DEV)[None, :] < lens[:, None])[..., None]
+    ref = (resid.reshape(B, Nseq, C) + torch.where(valid, y, torch.zeros_like(y))).reshape(M, C)
+    assert rel(out, ref) < 1e-5
+    assert torch.equal(out[~valid.expand(B, Nseq, C).reshape(M, C)], resid[~valid.expand(B, Nseq, C).reshape(M, C)])   # masked rows untouched
+    assert (raw[0] == 777.0).all() and (raw[M + 1] == 777.0).all()
+    if b16:
+        assert rel(outb[:M], ref) < 5e-3 and (outb[M] == -5.0).all()
+    if tma:
+        # one partial per 128 columns, whatever the tile configuration: partial p = sum of squares of columns [128 p, 128 p + 128)
+        want = torch.stack([(out[:, p * 128:(p + 1) * 128] ** 2).sum(1) for p in range(ss.shape[0])])
+        assert rel(ss, want) < 1e-5
+
+
+def test_resid_row_sums_do_not_depend_on_the_tiling():
+    """The same rows give bit-identical row-sum partials and results whether the launch takes 128-wide tiles (few rows) or 256-wide
+    tiles with 8 or 4 epilogue warps (many rows): a clip's latent must not depend on the batch it is sampled in."""
+    Nseq, K, C = 200, 1024, 1024
+    outs = []
+    for B in (2, 12):
+        M = B * Nseq
+        g = torch.Generator(device='cpu').manual_seed(77)
+        a1 = bf(torch.randn(2 * Nseq, K, generator=g)).to(DEV)
+        w = bf(torch.randn(C, K, generator=g) / math.sqrt(K)).to(DEV)
+        r1 = torch.randn(2 * Nseq, C, generator=g).to(DEV)
+        a = torch.cat([a1] + [torch.randn(Nseq, K, device=DEV).to(torch.bfloat16) for _ in range(B - 2)])
+        out = torch.cat([r1] + [torch.randn(Nseq, C, device=DEV) for _ in range(B - 2)]).contiguous()
+        ss = torch.zeros(8, M, device=DEV)
+        outb = torch.zeros(M, C, device=DEV, dtype=torch.bfloat16)
+        gemm(M, C, K, [a], w, _lib.EPI_RESID, out=out, ldo=C, resid=out, ldr=C, out_b16=outb, ldo_b16=C, row_ss=ss, row_ss_ld=M)
+        variant = list((ctypes.c_int * 3).in_dll(_lib.lib(), 'e2b_gemm_last_variant'))
+        outs.append((variant, out[:2 * Nseq].clone(), ss[:, :2 * Nseq].clone(), outb[:2 * Nseq].clone()))
+    assert outs[0][0][1] == 128 and outs[1][0][1] == 256, (outs[0][0], outs[1][0])
+    for x, y in zip(outs[0][1:], outs[1][1:]):
+        assert torch.equal(x, y)
+
+
+def test_resid_epilogue_row_sums_and_scaled_copy():
+    """Norm as a row scale: the TMA residual epilogue also emits sum(out^2) per row (partials per column tile and warp group) and
+    bf16(out * scale[col]) with a second scale vector from a split row on."""
+    B, Nseq, K, C = 9, 333, 1024, 1024
+    M = B * Nseq
+    a, w = _ab(M, C, K, 11)
+    resid = torch.randn(M, C, device=DEV)
+    gate = torch.rand(1, C, device=DEV)
+    s1, s2 = torch.rand(C, device=DEV) + 0.5, torch.rand(C, device=DEV) + 0.5
+    split = 1400
+    out = resid.clone()
+    outb = torch.zeros(M, C, device=DEV, dtype=torch.bfloat16)
+    d = _lib.GemmDesc()
+    d.N, d.K = C, K
+    parts = _lib.lib().e2b_gemm_row_parts(ctypes.byref(d))
+    assert parts == 8                                                     # 4 column tiles x 2 warp groups
+    ss = torch.full((parts, M), float('nan'), device=DEV)
+    gemm(M, C, K, [a], w, _lib.EPI_RESID, out=out, ldo=C, resid=out, ldr=C, gate=gate, gate_bstride=0, out_b16=outb, ldo_b16=C,
+         row_ss=ss, row_ss_ld=M, b16_scale=s1, b16_scale2=s2, b16_split_row=split)
+    ref = resid + (a.float() @ w.float().t()) * gate
+    assert rel(out, ref) < 1e-5
+    assert rel(ss.sum(0), (ref * ref).sum(1)) < 1e-5
+    scale = torch.where(torch.arange(M, device=DEV)[:, None] >= split, s2[None], s1[None])
+    assert rel(outb, ref * scale) < 5e-3
 
 
 def test_qkv_epilogue_rope_vt_gate():

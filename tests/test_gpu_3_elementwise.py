@@ -48,6 +48,30 @@ def test_dwconv(B, N, C_, lens):
     assert rel(y, ref) < 1e-5
 
 
+@pytest.mark.parametrize('B,N,C_,lens', [(2, 100, 192, [100, 63]), (3, 782, 1280, [782, 500, 40]), (1, 65, 64, [65]), (2, 130, 512, [130, 129])])
+def test_dwconv_with_normed_operand_outputs(B, N, C_, lens):
+    """Norm as a row scale, producing side in the conv kernel: same y as the plain kernel (bit for bit), plus bf16(y * gain) and the
+    sums of y^2 per row and 128-channel group."""
+    x = torch.randn(B, N, C_, device=DEV)
+    w = torch.randn(C_, 1, 31, device=DEV) / 5
+    b = torch.randn(C_, device=DEV)
+    gain = torch.rand(C_, device=DEV) + 0.5
+    lt = torch.tensor(lens, device=DEV, dtype=torch.int32)
+    wt = w[:, 0, :].t().contiguous()
+    y0 = torch.zeros_like(x)
+    kcheck(L().e2b_dwconv_launch(P(x), P(y0), P(wt), P(b), P(lt), B, N, C_, 31, sp()))
+    raw, y, pad = _guarded((B, N, C_))
+    rawb, yb, padb = _guarded((B * N, C_), torch.bfloat16)
+    parts = (C_ + 127) // 128
+    ss = torch.full((parts, B * N), float('nan'), device=DEV)
+    kcheck(L().e2b_dwconv_norm_launch(P(x), P(y), P(wt), P(b), P(lt), B, N, C_, 31, P(yb), P(gain), P(ss), B * N, sp()))
+    assert torch.equal(y, y0) and _guards_intact(raw, pad) and _guards_intact(rawb, padb)
+    yf = y.reshape(B * N, C_)
+    assert rel(yb, yf * gain) < 4e-3
+    want = torch.stack([(yf[:, p * 128:(p + 1) * 128] ** 2).sum(1) for p in range(parts)])
+    assert rel(ss, want) < 1e-5
+
+
 def test_time_conditioning():
     dim, nt, nmat = 128, 5, 4
     g = torch.Generator().manual_seed(0)

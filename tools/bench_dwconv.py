@@ -28,4 +28,19 @@ for C_ in (1024, 1280, 512):
     for _ in range(10): run()
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 100
+    # the variant that also writes the normed bf16 operand and the row sums, against conv + rmsnorm as two kernels
+    yb = torch.empty(B * N, C_, device=DEV, dtype=torch.bfloat16)
+    gain = torch.rand(C_, device=DEV) + 0.5
+    ss = torch.empty((C_ + 127) // 128, B * N, device=DEV)
+    runn = lambda: kcheck(L().e2b_dwconv_norm_launch(P(x), P(y), P(wt), P(b), P(lt), B, N, C_, 31, P(yb), P(gain), P(ss), B * N, sp()))
+    runr = lambda: kcheck(L().e2b_rmsnorm_launch(P(y), C_, P(yb), C_, P(gain), 0, B, N, 0, C_, 0, sp()))
+    def tm(fn):
+        for _ in range(3): fn()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10): fn()
+        a1.record(); torch.cuda.synchronize()
+        return a0.elapsed_time(a1) * 100
+    usn, usr = tm(runn), tm(runr)
+    print(f'   C={C_:5d}: conv+norm outputs {usn:7.1f} us  vs conv {us:7.1f} + rmsnorm {usr:7.1f} = {us + usr:7.1f} us')
     print(f'C={C_:5d}: {us:7.1f} us  {8.0 * B * N * C_ / us / 1e3:7.1f} GB/s  rel err {err:.1e}')

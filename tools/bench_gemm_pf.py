@@ -9,6 +9,8 @@ from e2_tts_pytorch import _lib
 from gpu_util import gemm, DEV
 M = 100096
 knob = C.c_int.in_dll(_lib.lib(), 'e2b_gemm_prefetch_kb')
+rt_knob = C.c_int.in_dll(_lib.lib(), 'e2b_gemm_resid_tma')
+MODE = os.environ.get('AB', 'resid')        # 'pf': A-operand prefetch distances; 'resid': TMA vs classic residual epilogue
 flush = torch.empty(256 * 1024 * 1024, device=DEV)
 
 
@@ -30,11 +32,20 @@ def timeit(N, K, epi, extra, srcs):
 def case(name, N, srcs, epi, mk):
     K = sum(srcs)
     row = f'{name:22s} N={N:5d} K={K:5d}:'
-    for pf in (0, 6, 12, 24):
-        knob.value = pf
-        us = timeit(N, K, epi, mk(), srcs)
-        row += f'  pf={pf:2d} {us:7.1f} us ({2 * M * N * K / us / 1e6:5.0f} TF/s)'
-    knob.value = 0
+    if MODE == 'pf':
+        for pf in (0, 6, 12, 24):
+            knob.value = pf
+            us = timeit(N, K, epi, mk(), srcs)
+            row += f'  pf={pf:2d} {us:7.1f} us ({2 * M * N * K / us / 1e6:5.0f} TF/s)'
+        knob.value = 0
+    else:
+        ex = mk()
+        nbytes = 2.0 * M * K + (8.0 * M * N if epi == _lib.EPI_RESID else 0) + (2.0 * M * N if 'out_b16' in ex else 0)
+        for rt in ((0, 1) if epi == _lib.EPI_RESID else (1,)):
+            rt_knob.value = rt
+            us = timeit(N, K, epi, ex, srcs)
+            row += f'  {"tma    " if rt else "classic"} {us:7.1f} us ({2 * M * N * K / us / 1e6:5.0f} TF/s, {nbytes / us / 1e3:5.0f} GB/s)'
+        rt_knob.value = 1
     print(row, flush=True)
 
 

@@ -90,11 +90,44 @@ constexpr int DW_G = 16;            // outputs per register-window step (two ste
 int make_tmap_generic(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims, const uint64_t* strides,
                       const uint32_t* box);
 
+// Sum over the 32 lanes of a warp of 16 per-lane values at once (transposing butterfly, 16 shuffles): on return lane l holds
+// the warp total of v[(l >> 1) & 15].  Fixed exchange pattern: deterministic.
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+  float t8[8], t4[4], t2[2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool hi = lane & 16;
+    const float recv = __shfl_xor_sync(0xffffffffu, hi ? v[i] : v[i + 8], 16);
+    t8[i] = (hi ? v[i + 8] : v[i]) + recv;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool hi = lane & 8;
+    const float recv = __shfl_xor_sync(0xffffffffu, hi ? t8[i] : t8[i + 4], 8);
+    t4[i] = (hi ? t8[i + 4] : t8[i]) + recv;
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool hi = lane & 4;
+    const float recv = __shfl_xor_sync(0xffffffffu, hi ? t4[i] : t4[i + 2], 4);
+    t2[i] = (hi ? t4[i + 2] : t4[i]) + recv;
+  }
+  const bool hi = lane & 2;
+  const float recv = __shfl_xor_sync(0xffffffffu, hi ? t2[0] : t2[1], 2);
+  const float one = (hi ? t2[1] : t2[0]) + recv;
+  return one + __shfl_xor_sync(0xffffffffu, one, 1);
+}
+
 // One thread: 32 consecutive outputs of one channel.  FULL = no row of the tile (halo included) is masked, which is every
 // tile except the last one of a sequence: the per-element length tests disappear from the hot loop.
-template <int KS, bool FULL>
+// NORM: the conv output feeds an RMSNorm and then a GEMM (e2_tts_crossatt3.py:1082-1084, 1122-1126): also emit the bf16 A operand
+// bf16(y * gain[c]) (lane pairs exchange values so that a lane stores two adjacent channels) and, per warp, the sums of y^2 over its
+// 32 channels for every row (wpart[g + row], written by the even lanes) -- the GEMM scales its accumulator rows by sqrt(C) / ||y||.
+template <int KS, bool FULL, bool NORM>
 __device__ __forceinline__ void dwconv_rows(const float* __restrict__ xs, float* __restrict__ yp, const float (&w)[KS], float bs, int C,
-                                            int row0 /*first input row of xs[0]*/, int out0 /*first output row*/, int len, int N) {
+                                            int row0 /*first input row of xs[0]*/, int out0 /*first output row*/, int len, int N,
+                                            __nv_bfloat16* __restrict__ ybp /*row out0, channel c & ~1*/, float gain, float* __restrict__ wpart,
+                                            int lane) {
   constexpr int HALO = KS - 1, HALF = KS / 2;
   auto ldx = [&](int j) -> float {
     if (FULL) return xs[(size_t)j * DW_C];
@@ -118,29 +151,52 @@ __device__ __forceinline__ void dwconv_rows(const float* __restrict__ xs, float*
 #pragma unroll
     for (int o = 0; o < DW_G; ++o) {
       if (FULL) {
-        yp[(size_t)(g + o) * C] = win[HALF + o] + silu(acc[o]);
+        acc[o] = win[HALF + o] + silu(acc[o]);
+        yp[(size_t)(g + o) * C] = acc[o];
       } else {
         const int r = out0 + g + o;
         // the residual uses the UNMASKED x (e2_tts_crossatt3.py:1082: conv(x, mask) + x)
-        if (r < N) yp[(size_t)(g + o) * C] = (r < len) ? win[HALF + o] + silu(acc[o]) : xs[(size_t)(HALF + g + o) * DW_C];
+        acc[o] = (r < len) ? win[HALF + o] + silu(acc[o]) : xs[(size_t)(HALF + g + o) * DW_C];
+        if (r < N) yp[(size_t)(g + o) * C] = acc[o];
       }
+    }
+    if constexpr (NORM) {
+      // bf16 copy: the even lane of a channel pair stores rows 0..7 of the window, the odd lane rows 8..15 -- one exchange and one
+      // full-warp 4-byte store per row pair, no divergence
+      const bool odd = lane & 1;
+#pragma unroll
+      for (int o = 0; o < DW_G / 2; ++o) {
+        const float lo = acc[o] * gain, hi = acc[o + DW_G / 2] * gain;
+        const float recv = __shfl_xor_sync(0xffffffffu, odd ? lo : hi, 1);
+        const int ro = odd ? o + DW_G / 2 : o;
+        const uint32_t pk = odd ? pack_bf16(recv, hi) : pack_bf16(lo, recv);
+        if (FULL || out0 + g + ro < N) *reinterpret_cast<uint32_t*>(ybp + (size_t)(g + ro) * C) = pk;
+      }
+#pragma unroll
+      for (int o = 0; o < DW_G; ++o) acc[o] *= acc[o];
+      const float tot = warp_reduce16(acc, lane);
+      if (!(lane & 1)) wpart[g + ((lane >> 1) & 15)] = tot;
     }
 #pragma unroll
     for (int j = 0; j < HALO; ++j) win[j] = win[j + DW_G];
   }
 }
 
-template <int KS>
+template <int KS, bool NORM>
 __global__ void __launch_bounds__(2 * DW_C, 2) dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmx, float* __restrict__ y,
                                                                  const float* __restrict__ wt, const float* __restrict__ bias,
-                                                                 const int* __restrict__ lens, int batch, int N, int C) {
+                                                                 const int* __restrict__ lens, int batch, int N, int C,
+                                                                 __nv_bfloat16* __restrict__ yb, const float* __restrict__ gain,
+                                                                 float* __restrict__ rss, int rss_ld) {
   constexpr int HALO = KS - 1, HALF = KS / 2, ROWS = DW_T + HALO;
   // no static shared memory: the dynamic window starts at offset 0 (128-byte alignment needed by the TMA destination) and
   // is used directly so loads stay LDS (a uintptr_t round-trip would make them generic LD.E)
-  extern __shared__ __align__(128) float buf[];               // 2 x [ROWS][DW_C], then two mbarriers
+  extern __shared__ __align__(128) float buf[];               // 2 x [ROWS][DW_C], then two mbarriers, then (NORM) 2 x [8 warps][32 rows]
   uint64_t* full = reinterpret_cast<uint64_t*>(buf + 2 * ROWS * DW_C);
+  float* wparts = buf + 2 * ROWS * DW_C + 4;
   const int tid = threadIdx.x & (DW_C - 1);       // channel inside the tile
   const int rhalf = threadIdx.x / DW_C;           // which 32-row half of the tile this thread produces
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cchunks = (C + DW_C - 1) / DW_C, rtiles = (N + DW_T - 1) / DW_T;
   const int per_chunk = batch * rtiles;           // tiles of one channel chunk: chunk-major order, so a CTA keeps its taps
   const int total = per_chunk * cchunks;
@@ -159,7 +215,7 @@ __global__ void __launch_bounds__(2 * DW_C, 2) dwconv_tma_kernel(const __grid_co
   if (threadIdx.x == 0 && (int)blockIdx.x < total) issue(blockIdx.x, 0);
 
   float w[KS];
-  float bs = 0.f;
+  float bs = 0.f, gn = 1.f;
   int wcc = -1;
   int it = 0;
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
@@ -173,17 +229,29 @@ __global__ void __launch_bounds__(2 * DW_C, 2) dwconv_tma_kernel(const __grid_co
 #pragma unroll
       for (int i = 0; i < KS; ++i) w[i] = __ldg(wt + (size_t)i * C + c);
       bs = __ldg(bias + c);
+      if (NORM) gn = gain ? __ldg(gain + c) : 1.f;
       wcc = cc;
     }
     mbar_wait(&full[s], (it >> 1) & 1);
-    if (c < C) {
+    float* wpart = wparts + (s * 8 + warp) * 32;  // this warp's row sums for this tile (double-buffered across tiles)
+    if (c < C) {                                  // whole warps: C is a multiple of 32 in NORM mode
       const int g0 = rhalf * (DW_T / 2);
       const float* xs = buf + (size_t)s * ROWS * DW_C + (size_t)g0 * DW_C + tid;      // xs[j * DW_C] = x[r0 + g0 - HALF + j]
       float* yp = y + ((size_t)b * N + r0 + g0) * C + c;
-      if (r0 + DW_T + HALF <= len) dwconv_rows<KS, true>(xs, yp, w, bs, C, r0 + g0 - HALF, r0 + g0, len, N);
-      else dwconv_rows<KS, false>(xs, yp, w, bs, C, r0 + g0 - HALF, r0 + g0, len, N);
+      __nv_bfloat16* ybp = NORM ? yb + ((size_t)b * N + r0 + g0) * C + (c & ~1) : nullptr;
+      if (r0 + DW_T + HALF <= len) dwconv_rows<KS, true, NORM>(xs, yp, w, bs, C, r0 + g0 - HALF, r0 + g0, len, N, ybp, gn, wpart, lane);
+      else dwconv_rows<KS, false, NORM>(xs, yp, w, bs, C, r0 + g0 - HALF, r0 + g0, len, N, ybp, gn, wpart, lane);
+    } else if (NORM) {
+      if (!(lane & 1)) { wpart[(lane >> 1) & 15] = 0.f; wpart[16 + ((lane >> 1) & 15)] = 0.f; }
     }
-    __syncthreads();     // everyone is done with buffer s before it is refilled two tiles later
+    __syncthreads();     // everyone is done with buffer s before it is refilled two tiles later; the warps' row sums are complete
+    if (NORM && threadIdx.x < DW_T) {
+      // the 128 channels of this tile, per row: the four channel warps of the row's half, in warp order (deterministic)
+      const int rr = threadIdx.x, hf = rr >> 5, wi = rr & 31;
+      const float* p = wparts + (s * 8 + hf * 4) * 32 + wi;
+      const float tot = ((p[0] + p[32]) + p[64]) + p[96];
+      if (r0 + rr < N) rss[(size_t)cc * rss_ld + (size_t)b * N + r0 + rr] = tot;
+    }
   }
 }
 
@@ -434,19 +502,30 @@ extern "C" int e2b_rmsnorm_launch(const float* x, int ldx, void* y, int ldy, con
 
 extern "C" int e2b_dwconv_launch(const float* x, float* y, const float* w, const float* bias, const int* lens, int batch, int N,
                                  int C, int ksize, cudaStream_t stream) {
+  return e2b_dwconv_norm_launch(x, y, w, bias, lens, batch, N, C, ksize, nullptr, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int e2b_dwconv_norm_launch(const float* x, float* y, const float* w, const float* bias, const int* lens, int batch, int N,
+                                      int C, int ksize, void* y_b16, const float* gain, float* row_ss, int row_ss_ld, cudaStream_t stream) {
   if (ksize != 31) { e2b_set_kernel_error("dwconv: kernel size %d unsupported (31 only)", ksize); return -1; }
   if (batch <= 0 || N <= 0) return 0;
   if (C % 4) { e2b_set_kernel_error("dwconv: C must be a multiple of 4"); return -1; }
+  const bool norm = y_b16 != nullptr;
+  if (norm && (C % 32 || !row_ss || row_ss_ld < batch * N || (reinterpret_cast<uintptr_t>(y_b16) & 3))) {
+    e2b_set_kernel_error("dwconv: the normed-operand outputs need C %% 32 == 0, row_ss and row_ss_ld >= batch * N");
+    return -1;
+  }
   CUtensorMap tm;
   const uint64_t dims[3] = {(uint64_t)C, (uint64_t)N, (uint64_t)batch};
   const uint64_t strides[2] = {(uint64_t)C * 4, (uint64_t)N * C * 4};
   const uint32_t box[3] = {DW_C, DW_T + 30, 1};
   if (make_tmap_generic(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, x, dims, strides, box)) return -1;
-  const int smem = 2 * (DW_T + 30) * DW_C * 4 + 16;
+  const int smem = 2 * (DW_T + 30) * DW_C * 4 + 16 + 2 * 8 * 32 * 4;
   static bool configured[E2B_MAX_DEVICES] = {false};
   bool& conf = configured[e2b_device_slot()];
   if (!conf) {
-    if (cudaFuncSetAttribute(dwconv_tma_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(dwconv_tma_kernel<31, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaFuncSetAttribute(dwconv_tma_kernel<31, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       e2b_set_kernel_error("dwconv: shared memory attribute failed");
       return -1;
     }
@@ -454,8 +533,12 @@ extern "C" int e2b_dwconv_launch(const float* x, float* y, const float* w, const
   }
   const int total = batch * ((N + DW_T - 1) / DW_T) * ((C + DW_C - 1) / DW_C);
   const int grid = total < 2 * 148 ? total : 2 * 148;
-  ProfScope ps(stream, "dwconv", (long long)batch * N, C, ksize, 2.0 * batch * N * (double)C * ksize, 8.0 * batch * N * (double)C);
-  dwconv_tma_kernel<31><<<grid, 2 * DW_C, smem, stream>>>(tm, y, w, bias, lens, batch, N, C);
+  ProfScope ps(stream, "dwconv", (long long)batch * N, C, ksize, 2.0 * batch * N * (double)C * ksize, (norm ? 10.0 : 8.0) * batch * N * (double)C);
+  if (norm)
+    dwconv_tma_kernel<31, true><<<grid, 2 * DW_C, smem, stream>>>(tm, y, w, bias, lens, batch, N, C, reinterpret_cast<__nv_bfloat16*>(y_b16), gain,
+                                                                   row_ss, row_ss_ld);
+  else
+    dwconv_tma_kernel<31, false><<<grid, 2 * DW_C, smem, stream>>>(tm, y, w, bias, lens, batch, N, C, nullptr, nullptr, nullptr, 0);
   return check_launch("dwconv");
 }
 
@@ -533,6 +616,20 @@ extern "C" int e2b_cast_part_launch(const float* src, int lds, void* dst, int ld
   return check_launch("cast_part");
 }
 
+namespace e2b {
+__global__ void __launch_bounds__(256) scale_cols_kernel(const float* __restrict__ src, const float* __restrict__ gain, float* __restrict__ dst,
+                                                         size_t total, int cols) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i] * gain[i % cols];
+}
+}  // namespace e2b
+
+extern "C" int e2b_scale_cols_launch(const float* src, const float* gain, float* dst, int rows, int cols, cudaStream_t stream) {
+  const size_t total = (size_t)rows * cols;
+  if (!total) return 0;
+  e2b::scale_cols_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, gain, dst, total, cols);
+  return check_launch("scale_cols");
+}
+
 extern "C" int e2b_cast_pad_launch(const float* src, int lds, void* dst, int ldd, int rows, int C, cudaStream_t stream) {
   const size_t total = (size_t)rows * ldd;
   if (!total) return 0;
@@ -567,7 +664,9 @@ extern "C" int e2b_guided_euler_inpaint_launch(float* y, const float* pred, int 
   }
   const size_t total4 = pass_stride / 4;
   ProfScope ps(stream, "guided_euler", P, B, per_sample, 2.0 * P * pass_stride, 4.0 * pass_stride * (P + 2) + 2.0 * pass_stride * n_copies);
-  guided_euler_kernel<<<grid_for(total4, 256), 256, 0, stream>>>(y, pred, P, pass_stride, per_sample, total4, gw, dt, apg,
+  // one float4 per thread (no grid-stride loop): a 20-50 us kernel lives on memory-level parallelism, and the capped grid left
+  // each thread walking 2-3 dependent load -> store rounds (2.4 TB/s at C2; tools/bench_hbm_kernels.py)
+  guided_euler_kernel<<<grid_for(total4, 256, 1 << 22), 256, 0, stream>>>(y, pred, P, pass_stride, per_sample, total4, gw, dt, apg,
                                                                 keep_parallel, scratch, reinterpret_cast<__nv_bfloat16*>(y_b16), n_copies,
                                                                 inpaint, inpaint_lens, row_elems / 4);
   return check_launch("guided_euler");

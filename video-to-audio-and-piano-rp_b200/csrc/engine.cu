@@ -2,6 +2,7 @@
 // and the CFM sampler loop.  Host-side C++ only (no torch); see include/e2b.h for the C-ABI and the reference
 // lines each entry replaces.  Layer dataflow follows Transformer.forward, e2_tts_crossatt3.py:941-1143:
 //   text -> frames -> cross-condition -> U-Net skip -> conv -> self-attn -> cross-attn(T5) -> GEGLU FF.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -54,6 +55,7 @@ struct e2b_handle {
 
   // global weights
   float *registers = nullptr, *t_registers = nullptr, *f_registers = nullptr, *abs_pos = nullptr, *final_g = nullptr;
+  float* ones = nullptr;           // [max stream width] of 1.0: the gain of a norm whose g has been folded into the next weight
   float *fourier_w = nullptr, *time_w1 = nullptr, *time_b1 = nullptr;
   float *proj_in_b = nullptr, *to_pred_b = nullptr, *pf_b = nullptr;
   bf16 *proj_in_w = nullptr, *to_pred_w = nullptr, *pf_w = nullptr;
@@ -86,6 +88,12 @@ struct e2b_handle {
   double* apg_scratch = nullptr;
   int *lens_dev = nullptr, *ctx_lens_dev = nullptr, *cond_lens_dev = nullptr;
   unsigned char* drop_clip_dev = nullptr;
+  // norm as a row scale (bf16 mode): the residual GEMM that produces a stream value also emits its row sums of squares (rss) and the
+  // bf16 A operand of the next GEMM, which scales its accumulator rows -- no rmsnorm launch between them
+  bool fuse_conv = false;          // conv -> norm -> QKV fused as well (the conv kernel emits the normed operand; E2B_FUSE_CONV)
+  bool fuse_side = false;          // text / frames FF norm fused (decided at create: bf16 mode and the TMA residual epilogue enabled)
+  bool fuse_norm = false;          // audio-stream norms fused too (per call: time conditioning shared by the batch)
+  float* rss = nullptr;            // [RSS_PARTS, M]
   bool audio_cond = false;         // in-painting call: condbf / condm / cond_lens_dev are live
   bf16* condbf = nullptr;          // [P, B, n, num_channels] bf16 A operand of cond_proj_in: where(cond_mask, cond, 0), 0 for dropped passes
   float* condm = nullptr;          // [B, n, num_channels] the condition itself, for the final where(cond_mask, cond, out)
@@ -139,6 +147,7 @@ void free_pool(std::vector<void*>& pool) {
 }
 
 inline int rup(int v, int m) { return (v + m - 1) / m * m; }
+constexpr int RSS_PARTS = 16;      // upper bound of e2b_gemm_row_parts for this model family (N <= 2048)
 
 struct WMap {
   std::map<std::string, const e2b_tensor*> m;
@@ -236,17 +245,28 @@ int pack_concat(e2b_handle* h, const WMap& w, const std::vector<std::pair<std::s
 }
 
 // GEGLU interleave: packed tile of 256 rows = 128 value rows then the matching 128 gate rows.
-int pack_geglu(e2b_handle* h, const WMap& w, const std::string& base, int dim, int inner, bf16** wd, float** bd, cudaStream_t st) {
+// col_gain != nullptr: W[:, k] *= gain[k] before the bf16 rounding -- the static RMSNorm gain g of the preceding norm folded into
+// the weight, so that the A operand of this GEMM can be the plain bf16 copy of the stream (norm as a row scale)
+int pack_geglu(e2b_handle* h, const WMap& w, const std::string& base, int dim, int inner, bf16** wd, float** bd, cudaStream_t st,
+               const float* col_gain = nullptr) {
   const e2b_tensor *tw, *tb;
   if (need(h, w, base + ".weight", &tw, 2 * inner, dim) || need(h, w, base + ".bias", &tb, 2 * inner)) return -1;
   if (inner % 128) return fail(h, "GEGLU inner dim %d must be a multiple of 128", inner);
+  const float* wsrc = tw->dev;
+  float* scaled = nullptr;
+  if (col_gain) {
+    if (cudaMalloc(&scaled, (size_t)2 * inner * dim * sizeof(float)) != cudaSuccess) return fail(h, "load_weights: temporary for the gain-folded GEGLU weight");
+    if (e2b_scale_cols_launch(tw->dev, col_gain, scaled, 2 * inner, dim, st) != 0) { cudaFree(scaled); return fail(h, "scale_cols: %s", e2b_kernel_last_error()); }
+    wsrc = scaled;
+  }
+  struct Free { float* p; cudaStream_t st; ~Free() { if (p) { cudaStreamSynchronize(st); cudaFree(p); } } } free_scaled{scaled, st};
   const std::vector<KBlock> blocks = {{dim, dim}};
   const int ldd = packed_k(h, blocks);
   DA(h->wallocs, *wd, (size_t)2 * inner * ldd);
   DA(h->wallocs, *bd, (size_t)2 * inner);
   for (int t = 0; t < inner / 128; ++t) {
-    if (cast_weight_rows(h, tw->dev, dim, t * 128, 128, *wd, ldd, t * 256, blocks, st)) return -1;
-    if (cast_weight_rows(h, tw->dev, dim, inner + t * 128, 128, *wd, ldd, t * 256 + 128, blocks, st)) return -1;
+    if (cast_weight_rows(h, wsrc, dim, t * 128, 128, *wd, ldd, t * 256, blocks, st)) return -1;
+    if (cast_weight_rows(h, wsrc, dim, inner + t * 128, 128, *wd, ldd, t * 256 + 128, blocks, st)) return -1;
     CU(cudaMemcpyAsync(*bd + t * 256, tb->dev + t * 128, 128 * 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(*bd + t * 256 + 128, tb->dev + inner + t * 128, 128 * 4, cudaMemcpyDeviceToDevice, st));
   }
@@ -271,7 +291,8 @@ int pack_stream(e2b_handle* h, const WMap& w, const std::string& p, int C, int h
   if (copy_f32(h, w, p + "2.to_v_head_gate.bias", &s.hg_b, heads, -1, st)) return -1;
   if (pack_linear(h, w, p + "2.to_out.weight", &s.out_w, C, HDs, st)) return -1;
   if (copy_f32(h, w, p + "3.g", &s.g2, C, -1, st)) return -1;
-  if (pack_geglu(h, w, p + "4.ff.0.proj", C, inner, &s.ff1_w, &s.ff1_b, st)) return -1;
+  // bf16 mode: the FF norm of the text / frames streams runs as a row scale, its static gain g is folded into the FF1 weight
+  if (pack_geglu(h, w, p + "4.ff.0.proj", C, inner, &s.ff1_w, &s.ff1_b, st, h->fuse_side ? s.g2 : nullptr)) return -1;
   if (pack_linear(h, w, p + "4.ff.2.weight", &s.ff2_w, C, inner, st)) return -1;
   return copy_f32(h, w, p + "4.ff.2.bias", &s.ff2_b, C, -1, st);
 }
@@ -345,7 +366,8 @@ int compute_time_tables(e2b_handle* h, const float* times_host, int nt, cudaStre
 
 // q/k/v(+gate) projection of `nb` followed by attention; result in h->ob.  kv = nullptr: self attention over `batch`
 // sequences; otherwise cross attention to the precomputed context K/V of layer `l`.
-int attention_block(e2b_handle* h, int C, int heads, const bf16* w_q, const float* hg_b, int batch, int layer_ctx, cudaStream_t st) {
+int attention_block(e2b_handle* h, int C, int heads, const bf16* w_q, const float* hg_b, int batch, int layer_ctx, cudaStream_t st,
+                    int in_parts = 0) {
   const int HDs = heads * 64;
   const bool cross = layer_ctx >= 0;
   const size_t rows = (size_t)batch * h->N;
@@ -357,6 +379,7 @@ int attention_block(e2b_handle* h, int C, int heads, const bf16* w_q, const floa
   d.q_scale = 0.125f;
   d.rope = h->rope; d.pos_off = 0; d.rows_per_batch = h->N;
   d.hgate = h->hg; d.hgate_ld = heads; d.hgate_bias = hg_b;
+  if (in_parts > 0) { d.in_row_ss = h->rss; d.in_row_parts = in_parts; d.in_row_ss_ld = (int)h->M; d.in_row_mult = sqrtf((float)C); }
   if (!h->f32) {
     d.out = h->qk;
     d.vt = h->vt; d.vt_ld = h->v_rows ? HDs : h->Npad; d.heads_v = heads; d.v_rowmajor = h->v_rows;
@@ -412,21 +435,38 @@ int attention_block(e2b_handle* h, int C, int heads, const bf16* w_q, const floa
 int side_stream(e2b_handle* h, float* (&s)[2], bf16* sb, int C, int heads, int inner, const Stream3& w, cudaStream_t st, const char* name) {
   e2b::NvtxRange range(name);
   const int HDs = heads * 64;
-  CK(e2b_dwconv_launch(s[0], s[1], w.conv_w, w.conv_b, h->lens_dev, h->Bt, h->N, C, h->cfg.kernel_size, st));
-  std::swap(s[0], s[1]);
-  if (norm(h, s[0], C, h->nb, w.g1, 0, h->Bt, 0, st)) return -1;
-  if (attention_block(h, C, heads, w.qkv_w, w.hg_b, h->Bt, -1, st)) return -1;
+  const int conv_parts = (C + 127) / 128;
+  if (h->fuse_conv && C % 32 == 0 && conv_parts <= RSS_PARTS) {
+    // conv -> RMSNorm -> QKV with the norm as a row scale: the conv kernel also leaves bf16(y * g1) and the row sums of squares
+    CK(e2b_dwconv_norm_launch(s[0], s[1], w.conv_w, w.conv_b, h->lens_dev, h->Bt, h->N, C, h->cfg.kernel_size, h->nb, w.g1, h->rss, (int)h->M, st));
+    std::swap(s[0], s[1]);
+    if (attention_block(h, C, heads, w.qkv_w, w.hg_b, h->Bt, -1, st, conv_parts)) return -1;
+  } else {
+    CK(e2b_dwconv_launch(s[0], s[1], w.conv_w, w.conv_b, h->lens_dev, h->Bt, h->N, C, h->cfg.kernel_size, st));
+    std::swap(s[0], s[1]);
+    if (norm(h, s[0], C, h->nb, w.g1, 0, h->Bt, 0, st)) return -1;
+    if (attention_block(h, C, heads, w.qkv_w, w.hg_b, h->Bt, -1, st)) return -1;
+  }
+  int parts = 0;                  // > 0: the out-projection left the FF norm's row statistics and A operand behind
   {
     e2b_gemm_desc d = gdesc(h, h->M, C, {{h->ob, HDs}}, w.out_w);
     d.epi = E2B_EPI_RESID;
     d.out = s[0]; d.ldo = C; d.resid = s[0]; d.ldr = C;
     d.lens = h->lens_dev; d.rows_per_batch = h->N;
+    if (h->fuse_side && e2b_gemm_resid_uses_tma(&d) && e2b_gemm_row_parts(&d) <= RSS_PARTS) {
+      // norm as a row scale: bf16(x) (the gain g2 lives in the FF1 weight) + row sums of squares, no rmsnorm launch
+      d.out_b16 = h->nb; d.ldo_b16 = C;
+      d.row_ss = h->rss; d.row_ss_ld = (int)h->M;
+      parts = e2b_gemm_row_parts(&d);
+    }
     CK(e2b_gemm_launch(&d, st));
   }
-  if (norm(h, s[0], C, h->nb, w.g2, 0, h->Bt, 0, st)) return -1;
+  // the gain of this norm is folded into ff1_w whenever fuse_side is on, also when this launch shape took the classic epilogue
+  if (!parts && norm(h, s[0], C, h->nb, h->fuse_side ? h->ones : w.g2, 0, h->Bt, 0, st)) return -1;
   {
     e2b_gemm_desc d = gdesc(h, h->M, 2 * inner, {{h->nb, C}}, w.ff1_w);
     d.epi = E2B_EPI_GEGLU; d.bias = w.ff1_b; d.out = h->hb; d.ldo = ldb(h, inner); d.split = spl(h, inner);
+    if (parts) { d.in_row_ss = h->rss; d.in_row_parts = parts; d.in_row_ss_ld = (int)h->M; d.in_row_mult = sqrtf((float)C); }
     CK(e2b_gemm_launch(&d, st));
   }
   {
@@ -448,6 +488,9 @@ int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
   const int ctx_batch = h->Pctx * h->B;
   const size_t Mc = (size_t)ctx_batch * h->N;
   auto G = [&](int layer, int which) { return gam.p + (size_t)(layer * 6 + which) * dim; };
+  // audio-stream norms as row scales: bf16 mode, TMA residual epilogue on, and one time-conditioning vector for the whole batch
+  // (e2b_sample / e2b_forward; Transformer.forward with per-item times keeps the rmsnorm kernel)
+  const bool fuse = h->fuse_side && gam.bstride == 0;
 
   for (int l = 0; l < c.depth; ++l) {
     const LayerW& w = h->L[l];
@@ -486,38 +529,68 @@ int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
       CK(e2b_gemm_launch(&d, st));
     }
     // audio stream
+    int parts = 0;                 // > 0: the self-attention out-projection left the next norms' statistics and operands behind
+    bool parts_ff_ok = true;
     {
       e2b::NvtxRange r("e2b.audio.self_attn");
-      CK(e2b_dwconv_launch(h->x[0], h->x[1], w.conv_w, w.conv_b, h->lens_dev, h->Bt, h->N, dim, c.kernel_size, st));
-      std::swap(h->x[0], h->x[1]);
-      if (norm(h, h->x[0], dim, h->nb, G(l, 0), gam.bstride, h->Bt, 0, st)) return -1;
-      if (attention_block(h, dim, H, w.qkv_w, w.hg_b, h->Bt, -1, st)) return -1;
+      if (fuse && h->fuse_conv && dim % 32 == 0 && (dim + 127) / 128 <= RSS_PARTS) {
+        CK(e2b_dwconv_norm_launch(h->x[0], h->x[1], w.conv_w, w.conv_b, h->lens_dev, h->Bt, h->N, dim, c.kernel_size, h->nb, G(l, 0), h->rss, (int)M, st));
+        std::swap(h->x[0], h->x[1]);
+        if (attention_block(h, dim, H, w.qkv_w, w.hg_b, h->Bt, -1, st, (dim + 127) / 128)) return -1;
+      } else {
+        CK(e2b_dwconv_launch(h->x[0], h->x[1], w.conv_w, w.conv_b, h->lens_dev, h->Bt, h->N, dim, c.kernel_size, st));
+        std::swap(h->x[0], h->x[1]);
+        if (norm(h, h->x[0], dim, h->nb, G(l, 0), gam.bstride, h->Bt, 0, st)) return -1;
+        if (attention_block(h, dim, H, w.qkv_w, w.hg_b, h->Bt, -1, st)) return -1;
+      }
       {
         e2b_gemm_desc d = gdesc(h, M, dim, {{h->ob, HD}}, w.out_w);
         d.epi = E2B_EPI_RESID;
         d.out = h->x[0]; d.ldo = dim; d.resid = h->x[0]; d.ldr = dim;
         d.gate = G(l, 1); d.gate_bstride = gam.bstride;
         d.lens = h->lens_dev; d.rows_per_batch = h->N;
+        if (fuse && e2b_gemm_resid_uses_tma(&d) && e2b_gemm_row_parts(&d) <= RSS_PARTS) {
+          // The out-projection produces the input of the NEXT norm: rows of context-live passes go on to the cross-attention
+          // (AdaptiveRMSNorm gain gamma2 + 1), the others straight to the feed-forward (gamma3 + 1).  It leaves bf16(x * gain) and
+          // the row sums of squares; the consuming GEMM scales its accumulator rows by sqrt(dim) / ||x||.
+          d.out_b16 = h->nb; d.ldo_b16 = dim;
+          d.b16_scale = Mc > 0 ? G(l, 2) : G(l, 4); d.b16_scale2 = G(l, 4); d.b16_split_row = (int)Mc;
+          d.row_ss = h->rss; d.row_ss_ld = (int)M;
+          parts = e2b_gemm_row_parts(&d);
+        }
         CK(e2b_gemm_launch(&d, st));
       }
     }
     // cross attention to the T5 context: only for passes whose context is live (a zero context gives exactly 0)
     if (Mc > 0) {
       e2b::NvtxRange r("e2b.audio.cross_attn");
-      if (norm(h, h->x[0], dim, h->nb, G(l, 2), gam.bstride, ctx_batch, 0, st)) return -1;
-      if (attention_block(h, dim, H, w.q2_w, w.hg2_b, ctx_batch, l, st)) return -1;
+      if (!parts && norm(h, h->x[0], dim, h->nb, G(l, 2), gam.bstride, ctx_batch, 0, st)) return -1;
+      if (attention_block(h, dim, H, w.q2_w, w.hg2_b, ctx_batch, l, st, parts)) return -1;
       e2b_gemm_desc o = gdesc(h, Mc, dim, {{h->ob, HD}}, w.out2_w);
       o.epi = E2B_EPI_RESID;
       o.out = h->x[0]; o.ldo = dim; o.resid = h->x[0]; o.ldr = dim;
       o.gate = G(l, 3); o.gate_bstride = gam.bstride;
       o.lens = h->lens_dev; o.rows_per_batch = h->N;
+      if (parts) {
+        // these rows now carry the cross-attention update: rewrite their FF-norm operand and statistics.  The launch must take the
+        // same epilogue variant as the out-projection (same N and K: same number of partials); otherwise fall back below.
+        if (e2b_gemm_resid_uses_tma(&o) && e2b_gemm_row_parts(&o) == parts) {
+          o.out_b16 = h->nb; o.ldo_b16 = dim;
+          o.b16_scale = G(l, 4);
+          o.row_ss = h->rss; o.row_ss_ld = (int)M;
+        } else {
+          parts_ff_ok = false;
+        }
+      }
       CK(e2b_gemm_launch(&o, st));
     }
     e2b::NvtxRange ff_range("e2b.audio.ff");
-    if (norm(h, h->x[0], dim, h->nb, G(l, 4), gam.bstride, h->Bt, 0, st)) return -1;
+    const bool ff_fused = parts > 0 && parts_ff_ok;
+    if (!ff_fused && norm(h, h->x[0], dim, h->nb, G(l, 4), gam.bstride, h->Bt, 0, st)) return -1;
     {
       e2b_gemm_desc d = gdesc(h, M, 2 * h->inner, {{h->nb, dim}}, w.ff1_w);
       d.epi = E2B_EPI_GEGLU; d.bias = w.ff1_b; d.out = h->hb; d.ldo = ldb(h, h->inner); d.split = spl(h, h->inner);
+      if (ff_fused) { d.in_row_ss = h->rss; d.in_row_parts = parts; d.in_row_ss_ld = (int)M; d.in_row_mult = sqrtf((float)dim); }
       CK(e2b_gemm_launch(&d, st));
     }
     {
@@ -625,6 +698,13 @@ extern "C" int e2b_create(const e2b_config* cfg, e2b_handle** out) {
   h->nmat = cfg->depth * 6;
   h->f32 = cfg->precision == 1;
   {
+    // norm as a row scale needs the TMA-based residual epilogue (bf16 mode; E2B_RESID_TMA=0 or E2B_FUSE_NORM=0 switch it off)
+    const char *r = getenv("E2B_RESID_TMA"), *f = getenv("E2B_FUSE_NORM");
+    h->fuse_side = !h->f32 && !(r && r[0] == '0') && !(f && f[0] == '0');
+    const char* cv = getenv("E2B_FUSE_CONV");
+    h->fuse_conv = h->fuse_side && !(cv && cv[0] == '0');
+  }
+  {
     const char *a = getenv("E2B_ATTN"), *v = getenv("E2B_VT");
     const bool v1 = a && (a[0] == 'v' ? a[1] == '1' : a[0] == '1');
     h->v_rows = !(v1 || (v && v[0] == '1'));
@@ -667,6 +747,12 @@ extern "C" int e2b_load_weights(e2b_handle* h, const e2b_tensor* tensors, int n,
   const std::string T = "transformer.";
   const int dim = c.dim, dt = c.dim_text, df = c.dim_frames, H = c.heads, HD = h->HD;
 
+  {
+    const int cmax = std::max(dim, std::max(dt, df));
+    std::vector<float> one(cmax, 1.0f);
+    DA(h->wallocs, h->ones, cmax);
+    CU(cudaMemcpy(h->ones, one.data(), cmax * sizeof(float), cudaMemcpyHostToDevice));
+  }
   if (copy_f32(h, w, T + "registers", &h->registers, c.num_registers, dim, st)) return -1;
   if (copy_f32(h, w, T + "text_registers", &h->t_registers, c.num_registers, dt, st)) return -1;
   if (copy_f32(h, w, T + "frames_registers", &h->f_registers, c.num_registers, df, st)) return -1;
@@ -853,6 +939,7 @@ static int allocate_workspace(e2b_handle* h, int B, int n, int nc, int P) {
   DA(h->sallocs, h->ctx_lens_dev, B);
   DA(h->sallocs, h->drop_clip_dev, h->Bt);
   DA(h->sallocs, h->cond_lens_dev, B);
+  DA(h->sallocs, h->rss, (size_t)RSS_PARTS * M);
   DA(h->sallocs, h->condbf, (size_t)h->Bt * n * c.num_channels * w2);
   DA(h->sallocs, h->condm, (size_t)B * n * c.num_channels);
   h->B = B;                        // last: marks the workspace as complete

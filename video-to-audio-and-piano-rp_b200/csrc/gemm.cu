@@ -24,9 +24,13 @@ namespace e2b {
 constexpr int BM = 128;
 constexpr int BK = 64;
 
+// Internal epilogue id: E2B_EPI_RESID with the residual stream moved by the TMA unit (see rt_epilogue below).
+constexpr int EPI_RESID_TMA = 5;
+
 struct GemmArgs {
   CUtensorMap tmA[E2B_MAX_SRC];
   CUtensorMap tmB;
+  CUtensorMap tmR, tmO, tmO16;   // EPI_RESID_TMA: fp32 residual in, fp32 result out, bf16 copy out (boxes of 32 rows x 32 columns)
   CUtensorMap tmBt;          // ragged last column tile: the same W with a box of tail_rows rows (no zero-filled rows through the pipe)
   int tail_rows;             // 0: N is a multiple of the tile width (or the tail is a full box); else valid columns of the last tile, rounded up to 16
   int pf_kb;                 // A-operand L2 prefetch distance in 64-wide K blocks (0 = off)
@@ -37,14 +41,20 @@ struct GemmArgs {
 // EW = number of epilogue warps.  4: one per TMEM lane quarter, 4-stage operand ring (large K, MMA-bound).  8: two per
 // quarter taking alternate 32-column chunks, 3-stage ring: for K <= 1024 the epilogue (one warp per scheduler, IPC ~0.3)
 // is longer than the 8K-cycle mainloop of a tile, so thread-level parallelism in the epilogue is worth a pipeline stage.
-template <int BN, int EW>
+template <int BN, int EW, int EPI = 0>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? (EW == 8 ? 3 : 4) : 6;
   static constexpr int THREADS = 128 + 32 * EW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EW * 4608 /*epilogue transpose buffers*/ + 256 /*barriers*/;
+  // EPI_RESID_TMA: per epilogue warp RT_NBUF residual / result tiles of 32 x 32 fp32 (4 KB, SWIZZLE_128B) and one 32 x 32 bf16
+  // tile (2 KB, SWIZZLE_64B); then the gate and bias vectors of the current column tile (2 x BN floats)
+  static constexpr bool RT = (EPI == EPI_RESID_TMA);
+  static constexpr int RT_NBUF = (EW == 8) ? 2 : 1;
+  static constexpr int RT_WARP_BYTES = RT_NBUF * 4096 + 2048;
+  static constexpr int EPI_BYTES = RT ? EW * RT_WARP_BYTES + 2 * BN * 4 : EW * (4608 /*epilogue transpose buffer*/ + 128 /*row scales*/);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + (RT ? 128 : 0) /*residual-tile barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;   // 512 or 256: both powers of two
 };
 
@@ -125,9 +135,194 @@ struct EpiRows {
   bool valid[8];         // EPI_RESID row mask (valid length)
 };
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// EPI_RESID_TMA: out = resid + valid(row) * gate[col] * (acc + bias[col]) with the fp32 residual stream moved by the TMA unit.
+// The classic epilogue above spends its time in the load/store unit: per 32 x 32 chunk a lane issues 8 LDG.128 for the residual,
+// 16 STS/LDS for the transpose and 16 STG for the fp32 result and its bf16 copy, and stalls on the residual loads (ncu: LSU 62-68 %,
+// long-scoreboard the top stall; the K <= 1024 out-projections sit at 3.8 TB/s of algorithmic traffic, 58 % of the HBM peak).
+// Here a lane keeps the accumulator layout tcgen05.ld gives it -- one ROW of 32 columns -- and never touches global memory:
+//   * the residual chunk [32 rows x 32 columns fp32] arrives by a TMA load (one elected lane, issued a chunk ahead) in the 128-byte
+//     swizzled layout, in which the row-per-lane LDS.128 / STS.128 of a quarter warp hit 8 different 16-byte columns: conflict free;
+//   * the lane updates its row in place in shared memory, writes the bf16 copy of the row into a second (64-byte swizzled) tile,
+//     and one lane hands both tiles to TMA stores (full 128-byte lines, asynchronous, no registers, no L1 sectors);
+//   * gate and bias of the tile's columns are staged once per tile in shared memory and read as broadcasts;
+//   * because a lane owns whole rows, the row sums of squares that a following RMSNorm needs are lane-local: with d.row_ss set the
+//     epilogue also writes sum(out^2) of the columns it handled (one partial per column tile and epilogue-warp group) and, with
+//     d.b16_scale, the bf16 copy becomes bf16(out * scale[col]) -- the A operand of the next GEMM, which multiplies its accumulator
+//     rows by sqrt(C) / ||x|| (norm as a row scale: the rmsnorm launch and its 6 B / element round trip disappear).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int crd0, int crd1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory"); }
+
+template <int BN, int EW>
+__device__ __forceinline__ void rt_epilogue(const GemmArgs& args, uint8_t* sEpi, uint64_t* rfull_all, uint64_t* tfull, uint64_t* tempty,
+                                            uint32_t tmem_base, int warp, int lane, int total, int n_tiles) {
+  using Cfg = GemmCfg<BN, EW, EPI_RESID_TMA>;
+  constexpr int NBUF = Cfg::RT_NBUF;
+  constexpr int CSTEP = EW / 4;
+  const e2b_gemm_desc& d = args.d;
+  const int ew = warp & 3;      // TMEM lane quarter
+  // With 8 epilogue warps the two warps of a lane quarter split the tile's 32-column chunks into two CONTIGUOUS runs (not alternate
+  // chunks): a warp then owns whole 128-column groups, and the row sums of squares can be written per 128 columns -- the same
+  // partials, summed in the same order, whatever the tile width, warp count or row count of the launch (bit-identical results for a
+  // clip whatever the batch it is sampled in).
+  constexpr int CPW = BN / 32 / CSTEP;                              // chunks per warp
+  const int cw = warp >> 2;
+  const int c_first = cw * CPW;
+  uint8_t* rbuf = sEpi + warp * Cfg::RT_WARP_BYTES;                 // NBUF x 4 KB fp32 tiles (1024-byte aligned)
+  uint8_t* hbuf = rbuf + NBUF * 4096;                               // 2 KB bf16 tile
+  float* gvec = reinterpret_cast<float*>(sEpi + EW * Cfg::RT_WARP_BYTES);   // gate of the tile's columns
+  float* bvec = gvec + BN;                                                   // bias
+  uint64_t* rfull = rfull_all + warp * 2;
+  const bool per_batch_gate = d.gate && d.gate_bstride != 0;
+  const int sw7 = lane & 7, sw3 = (lane >> 1) & 3;                  // swizzle phases of this lane's row in the fp32 / bf16 tile
+
+  // running chunk sequence of this warp over all its tiles: chunk q lives in buffer q % NBUF, barrier phase (q / NBUF) & 1
+  int q_issue = 0, q_use = 0;
+  int it_tile = blockIdx.x, it_c = c_first;     // cursor of the next residual chunk to request
+  auto cursor_ok = [&]() { return it_tile < total; };
+  // (it_tile, it_c) -> the next chunk this warp really has: column chunks past the width of a ragged last tile do not exist
+  auto cursor_normalize = [&]() {
+    while (it_tile < total) {
+      if (it_c < c_first + CPW && (it_tile % n_tiles) * BN + it_c * 32 < d.N) break;
+      it_c = c_first;
+      it_tile += gridDim.x;
+      if (it_tile < total && (it_tile % n_tiles) * BN + c_first * 32 >= d.N) it_c = c_first + CPW;   // not even the first chunk: skip the tile
+    }
+  };
+  auto cursor_advance = [&]() {
+    ++it_c;
+    cursor_normalize();
+  };
+  auto issue_load = [&]() {                     // lane 0 only
+    const int m0 = (it_tile / n_tiles) * BM, n0 = (it_tile % n_tiles) * BN;
+    const int b = q_issue % NBUF;
+    mbar_arrive_expect_tx(&rfull[b], 4096);
+    tma_load_2d(rbuf + b * 4096, &args.tmR, &rfull[b], n0 + it_c * 32, m0 + ew * 32);
+  };
+  cursor_normalize();
+  if (cursor_ok()) {
+    if (lane == 0) issue_load();
+    ++q_issue;
+    cursor_advance();
+  }
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+    const int as = it & 1;
+    const uint32_t aphase = (it >> 1) & 1;
+    const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+    const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * BN;
+    const int ncols = min(BN, d.N - n0);
+    const int row = m0 + ew * 32 + lane;
+    bool valid = row < d.M;
+    const float* grow = nullptr;
+    if (valid && d.rows_per_batch > 0) {
+      const int b = row / d.rows_per_batch, pos = row - b * d.rows_per_batch;
+      if (d.lens) valid = pos < __ldg(d.lens + b);
+      if (per_batch_gate) grow = d.gate + (size_t)b * d.gate_bstride + n0;
+    }
+    // gate / bias of this tile's columns -> shared memory (all epilogue warps; the barriers keep tiles apart)
+    named_bar_sync(1, 32 * EW);
+    for (int i = warp * 32 + lane; i < BN; i += 32 * EW) {
+      const bool in = i < ncols;
+      gvec[i] = (in && d.gate && !per_batch_gate) ? __ldg(d.gate + n0 + i) : 1.0f;
+      bvec[i] = (in && d.bias) ? __ldg(d.bias + n0 + i) : 0.0f;
+    }
+    named_bar_sync(1, 32 * EW);
+    mbar_wait(&tfull[as], aphase);
+    tc_fence_after();
+    float ss = 0.f;                            // sum of squares of this row over the current 128-column group
+#pragma unroll 1
+    for (int c = c_first; c < c_first + CPW; ++c) {
+      if (c * 32 >= ncols) break;
+      const int b = q_use % NBUF;
+      const uint32_t ph = (q_use / NBUF) & 1;
+      // the stores of the previous chunk must have finished READING their tiles before the bf16 tile / the other fp32 tile is reused
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+      if constexpr (NBUF == 2) {                // request the next chunk's residual now: a whole chunk of latency cover
+        if (cursor_ok()) {
+          if (lane == 0) issue_load();
+          ++q_issue;
+          cursor_advance();
+        }
+      }
+      uint32_t v[32];
+      tmem_ld32(taddr + c * 32, v);
+      mbar_wait(&rfull[b], ph);
+      tmem_ld_wait();
+      uint8_t* rrow = rbuf + b * 4096 + lane * 128;
+      uint8_t* hrow = hbuf + lane * 64;
+      const float4* g4 = reinterpret_cast<const float4*>(gvec + c * 32);
+      const float4* b4 = reinterpret_cast<const float4*>(bvec + c * 32);
+      float sc = 0.f;                           // this chunk's 32 columns, in column order
+      const float4* s4 = d.b16_scale ? reinterpret_cast<const float4*>((row >= d.b16_split_row && d.b16_scale2 ? d.b16_scale2 : d.b16_scale) + n0 + c * 32) : nullptr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4* rp = reinterpret_cast<float4*>(rrow + ((j ^ sw7) * 16));
+        float4 r = *rp;
+        float4 gg = g4[j];
+        if (grow) gg = __ldg(reinterpret_cast<const float4*>(grow + c * 32) + j);
+        const float4 bb = b4[j];
+        if (valid) {
+          r.x = fmaf(__uint_as_float(v[4 * j + 0]) + bb.x, gg.x, r.x);
+          r.y = fmaf(__uint_as_float(v[4 * j + 1]) + bb.y, gg.y, r.y);
+          r.z = fmaf(__uint_as_float(v[4 * j + 2]) + bb.z, gg.z, r.z);
+          r.w = fmaf(__uint_as_float(v[4 * j + 3]) + bb.w, gg.w, r.w);
+        }
+        *rp = r;
+        // (columns past N in a ragged last chunk hold stale accumulator columns -- the narrow MMA never wrote them; the TMA store
+        // clips them, the row sums must skip them: N is a multiple of 4, so a float4 is live or dead as a whole)
+        if (c * 32 + 4 * j < ncols) sc = fmaf(r.x, r.x, fmaf(r.y, r.y, fmaf(r.z, r.z, fmaf(r.w, r.w, sc))));
+        if (d.out_b16) {
+          float4 o = r;
+          if (s4) { const float4 sc = __ldg(s4 + j); o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w; }
+          // 64-byte swizzle: 16-byte column (j / 2) of the row XOR ((row / 2) % 4); 8 bytes per j
+          *reinterpret_cast<uint2*>(hrow + (((j >> 1) ^ sw3) * 16) + (j & 1) * 8) = pack4_bf16(o);
+        }
+      }
+      fence_proxy_async_smem();                 // this lane's tile writes are visible to the TMA unit
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&args.tmO, rbuf + b * 4096, n0 + c * 32, m0 + ew * 32);
+        if (d.out_b16) tma_store_2d(&args.tmO16, hbuf, n0 + c * 32, m0 + ew * 32);
+        bulk_commit();
+      }
+      // canonical partials: ((chunk 0 + chunk 1) + chunk 2) + chunk 3 of every 128-column group
+      ss += sc;
+      if ((c & 3) == 3 || (c + 1) * 32 >= ncols) {
+        if (d.row_ss && row < d.M) d.row_ss[(size_t)((n0 >> 7) + (c >> 2)) * d.row_ss_ld + row] = ss;
+        ss = 0.f;
+      }
+      ++q_use;
+      if constexpr (NBUF == 1) {                // single tile: the next residual can only follow the store's read of this one
+        if (cursor_ok()) {
+          if (lane == 0) { bulk_wait_read0(); issue_load(); }
+          ++q_issue;
+          cursor_advance();
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty[as]);
+  }
+  if (lane == 0) bulk_wait0();                  // every store of this lane has landed before the CTA may exit
+  __syncwarp();
+}
+
 template <int BN, int EPI, int EW>
 __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_constant__ GemmArgs args) {
-  using Cfg = GemmCfg<BN, EW>;
+  using Cfg = GemmCfg<BN, EW, EPI>;
   // Used directly (no integer round-trip) so the compiler keeps the shared address space: the earlier manual 1024-byte
   // round-up through uintptr_t turned every access into generic LD.E/ST.E.  SWIZZLE_128B needs a 1024-byte aligned base;
   // with no static shared memory the dynamic window starts at offset 0 -- checked once below.
@@ -139,12 +334,13 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
   uint8_t* sEpi = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + EW * EPI_BUF_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + Cfg::EPI_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::STAGES;
   uint64_t* tfull = bars + 2 * Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rfull = bars + 32;                  // EPI_RESID_TMA: [EW][2] residual-tile barriers (byte offset 256)
 
   const e2b_gemm_desc& d = args.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -161,6 +357,11 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
     for (int s = 0; s < d.num_src; ++s) tma_prefetch_desc(&args.tmA[s]);
     tma_prefetch_desc(&args.tmB);
     if (args.tail_rows > 0) tma_prefetch_desc(&args.tmBt);
+    if constexpr (EPI == EPI_RESID_TMA) {
+      tma_prefetch_desc(&args.tmR);
+      tma_prefetch_desc(&args.tmO);
+      if (d.out_b16) tma_prefetch_desc(&args.tmO16);
+    }
   }
   if (warp == W_MMA && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -171,6 +372,8 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], EW);
     }
+    if constexpr (EPI == EPI_RESID_TMA)
+      for (int s = 0; s < 2 * EW; ++s) mbar_init(&rfull[s], 1);
     fence_mbar_init();
   }
   if (warp == W_ALLOC) {
@@ -257,12 +460,17 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
       }
     }
   } else if (warp < EW) {
+   if constexpr (EPI == EPI_RESID_TMA) {
+    rt_epilogue<BN, EW>(args, sEpi, rfull, tfull, tempty, tmem_base, warp, lane, total, n_tiles);
+   } else {
     // ------------------------------------------------------------ epilogue (TMEM -> regs -> smem transpose -> global)
     const int ewi = warp;
     const int ew = ewi & 3;    // == warp % 4: the TMEM lane quarter this warp may read
     const int cw = ewi >> 2;   // with 8 epilogue warps: which alternate 32-column chunks this warp takes
     constexpr int CSTEP = EW / 4;
     float4* buf = reinterpret_cast<float4*>(sEpi + ewi * EPI_BUF_BYTES);
+    float* rsv = reinterpret_cast<float*>(sEpi + EW * EPI_BUF_BYTES) + ewi * 32;    // row scale of this warp's 32 rows (norm as a row scale)
+    const bool rowscale = (EPI == E2B_EPI_GEGLU || EPI == E2B_EPI_QKV) && d.in_row_ss != nullptr;
     const int rsub = lane >> 3, cg = lane & 7;
     const float4* bufr = buf + rsub * EPI_PITCH4 + cg;          // + 4k * EPI_PITCH4 selects row 4k + rsub
     const bool per_batch_gate = (EPI == E2B_EPI_RESID) && d.gate && d.gate_bstride != 0;
@@ -321,6 +529,17 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
           }
         }
       }
+      if (rowscale) {
+        // RMSNorm of the A operand's rows as a scale of the accumulator rows: sqrt(C) / max(||x||, 1e-12), ||x||^2 from the partial
+        // sums the producing epilogue left (summed in a fixed order: deterministic)
+        const int row = m0 + ew * 32 + lane;
+        float s2 = 0.f;
+        if (row < d.M)
+          for (int p = 0; p < d.in_row_parts; ++p) s2 += __ldg(d.in_row_ss + (size_t)p * d.in_row_ss_ld + row);
+        __syncwarp();
+        rsv[lane] = d.in_row_mult / fmaxf(sqrtf(s2), 1e-12f);
+        __syncwarp();
+      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
 
@@ -351,7 +570,8 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const float4 a = bufr[4 * k * EPI_PITCH4];
-            const uint64_t one2 = f32x2_pack(1.0f, 1.0f);
+            const float rs = rowscale ? rsv[4 * k + rsub] : 1.0f;
+            const uint64_t one2 = f32x2_pack(rs, rs);            // the row scale rides on the bias fma
             const uint64_t g01 = gelu_erf2(f32x2_fma(f32x2_pack(gt[k].x, gt[k].y), one2, f32x2_pack(bg.x, bg.y)));
             const uint64_t g23 = gelu_erf2(f32x2_fma(f32x2_pack(gt[k].z, gt[k].w), one2, f32x2_pack(bg.z, bg.w)));
             const uint64_t o01 = f32x2_mul(f32x2_fma(f32x2_pack(a.x, a.y), one2, f32x2_pack(bv.x, bv.y)), g01);
@@ -385,8 +605,9 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
               const int b = row / d.rows_per_batch, pos = row - b * d.rows_per_batch;
               const int cc = col0 - d.k_end;
               __nv_bfloat16* vp = reinterpret_cast<__nv_bfloat16*>(d.vt) + ((size_t)(b * d.heads_v + (cc >> 6)) * 64 + (cc & 63)) * d.vt_ld + pos;
+              const float rs = rowscale ? rsv[lane] : 1.0f;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) vp[(size_t)i * d.vt_ld] = __float2bfloat16_rn(__uint_as_float(v[i]));
+              for (int i = 0; i < 32; ++i) vp[(size_t)i * d.vt_ld] = __float2bfloat16_rn(__uint_as_float(v[i]) * rs);
             }
             continue;
           }
@@ -394,10 +615,11 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
           __syncwarp();
           if (col0 < d.k_end) {
             // interleaved RoPE (x-transformers rotate_half on adjacent pairs): (x0,x1) -> (x0 c - x1 s, x1 c + x0 s)
-            const float sc = (col0 < d.q_end) ? d.q_scale : 1.0f;
+            const float sc0 = (col0 < d.q_end) ? d.q_scale : 1.0f;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               const float4 a = bufr[4 * k * EPI_PITCH4];
+              const float sc = rowscale ? sc0 * rsv[4 * k + rsub] : sc0;
               float4 o;
               o.x = (a.x * cs[k].x - a.y * cs[k].y) * sc;
               o.y = (a.y * cs[k].x + a.x * cs[k].y) * sc;
@@ -411,9 +633,12 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
           } else if (col0 < d.v_end && d.v_f32 == nullptr) {   // v as plain bf16 rows [M, vt_ld] (MN-major operand of the attention kernel)
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              if (R.out[k])
+              if (R.out[k]) {
+                float4 a = bufr[4 * k * EPI_PITCH4];
+                if (rowscale) { const float rs = rsv[4 * k + rsub]; a.x *= rs; a.y *= rs; a.z *= rs; a.w *= rs; }
                 *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.vt) + (size_t)(m0 + ew * 32 + 4 * k + rsub) * d.vt_ld + (col - d.k_end)) =
-                    pack4_bf16(bufr[4 * k * EPI_PITCH4]);
+                    pack4_bf16(a);
+              }
           } else if (col0 < d.v_end) {               // fp32 mode: v as plain fp32 [M, v_f32_ld]
 #pragma unroll
             for (int k = 0; k < 8; ++k)
@@ -422,8 +647,9 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
             const int gc = col - d.v_end;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              const float4 a = bufr[4 * k * EPI_PITCH4];
-              const float e[4] = {a.x, a.y, a.z, a.w};
+              const float4 a0 = bufr[4 * k * EPI_PITCH4];
+              const float rs = rowscale ? rsv[4 * k + rsub] : 1.0f;
+              const float e[4] = {a0.x * rs, a0.y * rs, a0.z * rs, a0.w * rs};
               if (R.out2[k]) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -525,6 +751,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);     // one arrival per epilogue warp
     }
+   }
   }
 
   tc_fence_before();
@@ -540,6 +767,11 @@ static thread_local char g_err[512] = "";
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace e2b
+// internal epilogue id, column tile width and epilogue warps of the most recent launch (tests assert which variant ran)
+extern "C" { int e2b_gemm_last_variant[3] = {-1, 0, 0}; }
+namespace e2b {
 
 static PFN_encodeTiled get_encode() {
   static PFN_encodeTiled fn = nullptr;
@@ -575,6 +807,19 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t col
   return 0;
 }
 
+// 2-D tiled map with a swizzle mode: dims / box innermost first, row stride in bytes
+int make_tmap_swizzled(CUtensorMap* m, CUtensorMapDataType dt, const void* base, const uint64_t* dims, const uint64_t* stride1, const uint32_t* box,
+                       CUtensorMapSwizzle sw) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { e2b_set_kernel_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
+  cuuint64_t gd[2] = {dims[0], dims[1]}, gs[1] = {stride1[0]};
+  cuuint32_t bx[2] = {box[0], box[1]}, es[2] = {1, 1};
+  CUresult r = enc(m, dt, 2, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { e2b_set_kernel_error("cuTensorMapEncodeTiled (swizzled 2-D) failed: %d", (int)r); return -1; }
+  return 0;
+}
+
 // generic tiled map (no swizzle): dims/box innermost first, strides in bytes for dims 1..rank-1
 int make_tmap_generic(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims, const uint64_t* strides,
                       const uint32_t* box) {
@@ -593,7 +838,7 @@ static int num_sms() { return e2b_num_sms(); }
 
 template <int BN, int EPI, int EW>
 static int launch_t(const GemmArgs& a, cudaStream_t st) {
-  using Cfg = GemmCfg<BN, EW>;
+  using Cfg = GemmCfg<BN, EW, EPI>;
   static bool configured[E2B_MAX_DEVICES] = {false};
   bool& conf = configured[e2b_device_slot()];
   if (!conf) {
@@ -603,11 +848,12 @@ static int launch_t(const GemmArgs& a, cudaStream_t st) {
   }
   const int tiles = ((a.d.M + BM - 1) / BM) * ((a.d.N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  static const char* kinds[] = {"gemm_bf16", "gemm_f32", "gemm_geglu", "gemm_resid", "gemm_qkv"};
+  static const char* kinds[] = {"gemm_bf16", "gemm_f32", "gemm_geglu", "gemm_resid", "gemm_qkv", "gemm_resid"};
   const double out_cols = (EPI == E2B_EPI_GEGLU) ? a.d.N / 2.0 : a.d.N;
-  const double out_bytes = (EPI == E2B_EPI_F32) ? 4.0 : (EPI == E2B_EPI_RESID ? 8.0 : 2.0);
+  const double out_bytes = (EPI == E2B_EPI_F32) ? 4.0 : ((EPI == E2B_EPI_RESID || EPI == EPI_RESID_TMA) ? 8.0 : 2.0);
   ProfScope ps(st, kinds[EPI], a.d.M, a.d.N, a.d.K, 2.0 * a.d.M * a.d.N * a.d.K,
                2.0 * ((double)a.d.M * a.d.K + (double)a.d.N * a.d.K) + out_bytes * a.d.M * out_cols + (a.d.out_b16 ? 2.0 * a.d.M * out_cols : 0.0));
+  e2b_gemm_last_variant[0] = EPI; e2b_gemm_last_variant[1] = BN; e2b_gemm_last_variant[2] = EW;
   gemm_kernel<BN, EPI, EW><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { e2b_set_kernel_error("gemm launch: %s", cudaGetErrorString(e)); return -1; }
@@ -627,9 +873,55 @@ extern "C" void e2b_set_kernel_error(const char* fmt, ...) {
 extern "C" const char* e2b_kernel_last_error(void) { return g_err; }
 
 // K threshold (inclusive) below which the 8-epilogue-warp configuration is used; settable for tuning / A-B tests.
+// EPI_RESID through the TMA-based epilogue (1, default) or the classic load/store one (0; E2B_RESID_TMA=0), and the largest K that
+// takes its 8-epilogue-warp / two-residual-tile configuration
+extern "C" int e2b_gemm_resid_tma = -1;
+
+extern "C" int e2b_gemm_resid_tma_ew8_max_k = 3072;
 // A-operand L2 prefetch distance in K blocks of 64 (0 = off); settable for A/B tests (E2B_GEMM_PF)
 extern "C" int e2b_gemm_prefetch_kb = -1;
 extern "C" int e2b_gemm_ew8_max_k = 1536;   // tools/bench_gemm3.py: 8 warps win up to K=1280, tie at 2048, lose at 5120
+
+static bool tile256(const e2b_gemm_desc* d) {
+  // Narrow outputs use 128-wide tiles; GEGLU needs the 128+128 packed 256 tile.
+  bool bn256 = (d->epi == E2B_EPI_GEGLU) || (d->N % 256 == 0) || (d->N > 1024);
+  if (bn256 && d->epi != E2B_EPI_GEGLU) {
+    // Few rows (one clip per call): when even the 128x128 tiling fits in one wave, the 128x256 tiling leaves most SMs idle
+    // (single 10 s clip: 52 tiles for 148 SMs at N = 1024) -- take the narrower tile (sample() latency 190 -> 166 ms).
+    const long long mt = (d->M + BM - 1) / BM;
+    if (mt * ((d->N + 127) / 128) <= e2b_num_sms()) bn256 = false;
+  }
+  return bn256;
+}
+
+static void read_env_knobs() {
+  if (e2b_gemm_resid_tma < 0) {
+    const char* e = getenv("E2B_RESID_TMA");
+    e2b_gemm_resid_tma = e ? atoi(e) : 1;
+  }
+  if (e2b_gemm_prefetch_kb < 0) {
+    const char* e = getenv("E2B_GEMM_PF");
+    e2b_gemm_prefetch_kb = e ? atoi(e) : 0;
+  }
+  static bool once = false;
+  if (!once) {
+    once = true;
+    const char* e = getenv("E2B_RT_EW8_MAXK");
+    if (e && atoi(e) > 0) e2b_gemm_resid_tma_ew8_max_k = atoi(e);
+  }
+}
+
+// does an EPI_RESID launch of this description take the TMA-based residual epilogue (the one that can emit row sums / a scaled copy)?
+extern "C" int e2b_gemm_resid_uses_tma(const e2b_gemm_desc* d) {
+  read_env_knobs();
+  return d->epi == E2B_EPI_RESID && e2b_gemm_resid_tma && d->resid && d->ldo % 4 == 0 && d->ldr % 4 == 0 &&
+         !(reinterpret_cast<uintptr_t>(d->out) & 15) && !(reinterpret_cast<uintptr_t>(d->resid) & 15) &&
+         (!d->out_b16 || (d->split == 0 && d->ldo_b16 % 8 == 0 && !(reinterpret_cast<uintptr_t>(d->out_b16) & 15)));
+}
+
+extern "C" int e2b_gemm_row_parts(const e2b_gemm_desc* d) {
+  return (d->N + 127) / 128;      // one partial per 128 columns, independent of the tile configuration the launch takes
+}
 
 extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
   if (d->M <= 0 || d->N <= 0) return 0;
@@ -647,15 +939,7 @@ extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
     a.kb_end[s] = (s < d->num_src) ? k / BK : (1 << 30);
   }
   if (k != d->K) { e2b_set_kernel_error("gemm: sum(ka)=%d != K=%d", k, d->K); return -1; }
-  // Narrow outputs use 128-wide tiles; GEGLU needs the 128+128 packed 256 tile.
-  bool bn256 = (d->epi == E2B_EPI_GEGLU) || (d->N % 256 == 0) || (d->N > 1024);
-  if (bn256 && d->epi != E2B_EPI_GEGLU) {
-    // Few rows (one clip per call): when even the 128x128 tiling fits in one wave, the 128x256 tiling leaves most SMs idle
-    // (single 10 s clip: 52 tiles for 148 SMs at N = 1024) -- take the narrower tile (sample() latency 190 -> 166 ms).
-    const int sms = e2b_num_sms();
-    const long long mt = (d->M + BM - 1) / BM;
-    if (mt * ((d->N + 127) / 128) <= sms) bn256 = false;
-  }
+  const bool bn256 = tile256(d);
   if (d->epi == E2B_EPI_GEGLU && d->N % 256) { e2b_set_kernel_error("gemm: GEGLU needs N %% 256 == 0 (N=%d)", d->N); return -1; }
   if (d->epi != E2B_EPI_QKV && (d->N % 4 || d->ldo % 4 || (d->out_b16 && d->ldo_b16 % 4) || (d->resid && d->ldr % 4) || (d->add_table && d->ld_add % 4) ||
                                 (d->gate && d->gate_bstride % 4))) {
@@ -666,10 +950,7 @@ extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
     e2b_set_kernel_error("gemm: QKV segment ends must be multiples of 64 and rows_per_batch > 0");
     return -1;
   }
-  if (e2b_gemm_prefetch_kb < 0) {
-    const char* e = getenv("E2B_GEMM_PF");
-    e2b_gemm_prefetch_kb = e ? atoi(e) : 0;
-  }
+  read_env_knobs();
   a.pf_kb = e2b_gemm_prefetch_kb;
   if (make_tmap_bf16(&a.tmB, d->w, d->N, d->K, d->ldw, bn256 ? 256 : 128)) return -1;
   {
@@ -685,6 +966,23 @@ extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
     case E2B_EPI_QKV: return launch_t<BN_, E2B_EPI_QKV, EW_>(a, stream);              \
     default: break;                                                                   \
   }
+  if (e2b_gemm_resid_uses_tma(d)) {
+    // residual stream through the TMA unit (row-per-lane epilogue); 8 epilogue warps with two residual tiles each up to K = 3072
+    const uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M};
+    const uint32_t box[2] = {32, 32};
+    const uint64_t sr[1] = {(uint64_t)d->ldr * 4}, so[1] = {(uint64_t)d->ldo * 4}, sh[1] = {(uint64_t)d->ldo_b16 * 2};
+    if (make_tmap_swizzled(&a.tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d->resid, dims, sr, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    if (make_tmap_swizzled(&a.tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d->out, dims, so, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    if (d->out_b16 && make_tmap_swizzled(&a.tmO16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d->out_b16, dims, sh, box, CU_TENSOR_MAP_SWIZZLE_64B)) return -1;
+    if (!bn256) return launch_t<128, EPI_RESID_TMA, 4>(a, stream);
+    if (d->K <= e2b_gemm_resid_tma_ew8_max_k) return launch_t<256, EPI_RESID_TMA, 8>(a, stream);
+    return launch_t<256, EPI_RESID_TMA, 4>(a, stream);
+  }
+  if (d->in_row_ss && ((d->epi != E2B_EPI_GEGLU && d->epi != E2B_EPI_QKV) || d->qk_f32 || d->in_row_parts <= 0)) {
+    e2b_set_kernel_error("gemm: in_row_ss (norm as a row scale) is for the bf16 GEGLU / QKV epilogues");
+    return -1;
+  }
+  if (d->row_ss || d->b16_scale) { e2b_set_kernel_error("gemm: row sums / scaled bf16 copy need the TMA residual epilogue (EPI_RESID, 16-byte aligned buffers, no hi/lo split)"); return -1; }
   const bool ew8 = d->K <= e2b_gemm_ew8_max_k;   // small K: epilogue-bound, use 8 epilogue warps + 3 stages
   if (bn256) {
     if (d->epi == E2B_EPI_GEGLU) return ew8 ? launch_t<256, E2B_EPI_GEGLU, 8>(a, stream) : launch_t<256, E2B_EPI_GEGLU, 4>(a, stream);

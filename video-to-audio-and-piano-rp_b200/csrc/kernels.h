@@ -60,9 +60,30 @@ typedef struct e2b_gemm_desc {
   int v_f32_ld;
   // EPI_QKV, bf16 mode: v_rowmajor != 0 stores v as plain rows, `vt` = bf16 [M, vt_ld] with column (packed col - k_end), instead of V^T
   int v_rowmajor;
+  // EPI_RESID, norm-as-row-scale (TMA epilogue only): row_ss != NULL receives the partial sums of squares of the fp32 result,
+  // row_ss[p * row_ss_ld + row] for p < e2b_gemm_row_parts(desc); b16_scale != NULL turns the bf16 copy into bf16(out * scale[col])
+  // (rows >= b16_split_row use b16_scale2 when it is set) -- together the A operand and the row statistics of a following RMSNorm
+  float* row_ss;
+  int row_ss_ld;
+  const float* b16_scale;
+  const float* b16_scale2;
+  int b16_split_row;
+  // EPI_GEGLU / EPI_QKV (bf16 mode), the consuming side: in_row_ss != NULL multiplies every accumulator row by
+  // in_row_mult / max(sqrt(sum_p in_row_ss[p * in_row_ss_ld + row]), 1e-12) before bias / RoPE / activation -- the RMSNorm of the A
+  // operand's rows (in_row_mult = sqrt(C)), whose per-column gain is already inside A (or folded into W)
+  const float* in_row_ss;
+  int in_row_parts;
+  int in_row_ss_ld;
+  float in_row_mult;
 } e2b_gemm_desc;
 
 int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream);
+// number of row_ss partials per row an EPI_RESID launch of this description writes (column tiles x epilogue-warp groups)
+int e2b_gemm_row_parts(const e2b_gemm_desc* d);
+// does an EPI_RESID launch of this description take the TMA-based residual epilogue (which row_ss / b16_scale require)?
+int e2b_gemm_resid_uses_tma(const e2b_gemm_desc* d);
+// dst[r, c] = src[r, c] * gain[c]
+int e2b_scale_cols_launch(const float* src, const float* gain, float* dst, int rows, int cols, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------------------
 // Flash-style attention with tanh soft-clamp, key-length mask and fused per-head gate.
@@ -119,6 +140,11 @@ int e2b_rmsnorm_launch(const float* x, int ldx, void* y, int ldy, const float* s
 // y = x + mask * silu(dwconv31(mask * x) + bias) over the sequence axis, channels-last [batch, N, C]; w is [K, C]
 int e2b_dwconv_launch(const float* x, float* y, const float* w /*[K,C] (transposed conv weight)*/, const float* bias, const int* lens,
                       int batch, int N, int C, int ksize, cudaStream_t stream);
+
+// The same, additionally emitting what the RMSNorm + GEMM that follow need (norm as a row scale): y_b16 [batch*N, C] = bf16(y * gain[c])
+// (gain NULL = 1) and row_ss[p * row_ss_ld + row] = sum of y^2 over channels [128 p, 128 p + 128), p < ceil(C / 128).  C % 32 == 0.
+int e2b_dwconv_norm_launch(const float* x, float* y, const float* w, const float* bias, const int* lens, int batch, int N, int C, int ksize,
+                           void* y_b16, const float* gain, float* row_ss, int row_ss_ld, cudaStream_t stream);
 
 // time conditioning: tcond[s,:] = silu(W1 * [t, sin(2pi t w), cos(2pi t w)] + b1) for nt times;
 // then for each of `nmat` matrices  out[s, m, :] = act_m(Wm * tcond[s] + bm)  (act: 0 => x+1 (AdaRMSNorm), 1 => sigmoid)

@@ -38,6 +38,8 @@ class GemmDesc(C.Structure):
         ('vt', C.c_void_p), ('vt_ld', C.c_int), ('heads_v', C.c_int),
         ('hgate', C.c_void_p), ('hgate_ld', C.c_int), ('hgate_bias', C.c_void_p),
         ('split', C.c_int), ('qk_f32', C.c_void_p), ('v_f32', C.c_void_p), ('v_f32_ld', C.c_int), ('v_rowmajor', C.c_int),
+        ('row_ss', C.c_void_p), ('row_ss_ld', C.c_int), ('b16_scale', C.c_void_p), ('b16_scale2', C.c_void_p), ('b16_split_row', C.c_int),
+        ('in_row_ss', C.c_void_p), ('in_row_parts', C.c_int), ('in_row_ss_ld', C.c_int), ('in_row_mult', C.c_float),
     ]
 
 
@@ -94,6 +96,7 @@ _SIGS = {
     'e2b_launch_count': (C.c_longlong, [C.c_void_p]),
     # kernel-level entry points (csrc/kernels.h) used by the unit tests
     'e2b_gemm_launch': (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    'e2b_gemm_row_parts': (C.c_int, [C.POINTER(GemmDesc)]),
     'e2b_attention_launch': (C.c_int, [C.POINTER(AttnDesc), C.c_void_p]),
     'e2b_attention_f32_launch': (C.c_int, [C.POINTER(AttnF32Desc), C.c_void_p]),
     'e2b_rmsnorm_launch': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -104,6 +107,8 @@ _SIGS = {
     'e2b_stage_clip': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'e2b_dwconv_launch': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_void_p]),
+    'e2b_dwconv_norm_launch': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'e2b_time_mlp_launch': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'e2b_time_gemv_launch': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                        C.c_void_p]),
