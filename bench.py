@@ -268,8 +268,12 @@ def main():
     kw = dict(steps=S, remove_parallel_component=False, sway_sampling=True, return_raw_output=True)
     kw.update(dict(cfg_strength=2.0) if guidance is None else dict(guidance=guidance))
 
+    compute_events = []                                          # per step: events around this rank's own sampling (collective excluded)
+
     def run_chunks(data, to_host):
         at = 0
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
         for i, d in enumerate(data):
             if to_host:
                 d = {k: v.to(dev, non_blocking=True) for k, v in d.items()}
@@ -279,6 +283,8 @@ def main():
             at += out.shape[0]
             if to_host:
                 out_host[i].copy_(out, non_blocking=True)
+        ev[1].record()
+        compute_events.append(ev)
         if world > 1:
             dist.all_gather_into_tensor(gathered, local_out)     # the path's only collective (equal shards: 512 % world == 0)
         return local_out
@@ -316,16 +322,19 @@ def main():
         step_resident()
     eng = model.engine()
     l0 = eng.launch_count()
+    del compute_events[:]
     with ClockSampler(local) as cs:
         ms = timed(step_resident, args.steps)
     launches = eng.launch_count() - l0
     clocks = cs.summary()
+    own_ms = sum(a.elapsed_time(b) for a, b in compute_events)   # this rank's sampling alone, without waiting for the other ranks
     per_rank = None
     if world > 1:                                                # attribution of the scaling loss: every rank's own time and clock
-        mhz = torch.tensor([clocks['sm_mhz'] or 0.0], device=dev)
-        every = [torch.zeros_like(mhz) for _ in range(world)]
-        dist.all_gather(every, mhz)
-        per_rank = dict(ms=rank_ms[0], sm_mhz_median=[float(v.item()) for v in every])
+        mine = torch.tensor([clocks['sm_mhz'] or 0.0, own_ms], device=dev)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank = dict(ms_timed_region=rank_ms[0], ms_own_sampling=[round(float(v[1].item()), 3) for v in every],
+                        sm_mhz_median=[float(v[0].item()) for v in every])
     audio_s = total_clips * (n / FRAME_RATE) * args.steps
     value = audio_s / (ms / 1e3)
 

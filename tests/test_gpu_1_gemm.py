@@ -221,6 +221,60 @@ def test_resid_epilogue_wide_tiles(B, Nseq, K, C, per_batch, b16, bias_on, tma):
         assert rel(ss, want) < 1e-5
 
 
+@pytest.mark.parametrize('K,ew', [(1024, 8), (3200, 4)])
+def test_cta_pair_variants_match_single_cta(K, ew):
+    """tcgen05 cta_group::2 (a CTA pair per 256-row tile, each CTA staging half of the B tile): GEGLU and TMA-residual GEMMs must
+    give bit-identical results to the one-CTA-per-tile kernels (same accumulation order), odd row-tile counts included."""
+    knob = ctypes.c_int.in_dll(_lib.lib(), 'e2b_gemm_cta_pair')
+    variant = (ctypes.c_int * 4).in_dll(_lib.lib(), 'e2b_gemm_last_variant')
+    M, C, inner = 128 * 47 + 57, 1024, 2048                               # 48 row tiles of 128 -> 24 pairs; the last rows are ragged
+    g = torch.Generator(device='cpu').manual_seed(K)
+    a = bf(torch.randn(M, K, generator=g)).to(DEV)
+    w = bf(torch.randn(C, K, generator=g) / math.sqrt(K)).to(DEV)
+    resid = torch.randn(M, C, generator=g).to(DEV)
+    gate, bias = torch.rand(1, C, device=DEV), torch.randn(C, device=DEV)
+    wg = bf(torch.randn(2 * inner, K, generator=g) / math.sqrt(K)).to(DEV)
+    bg = torch.randn(2 * inner, device=DEV)
+    H = 16
+    HD = H * 64
+    wq = bf(torch.randn(3 * HD + H, K, generator=g) / math.sqrt(K)).to(DEV)     # N = 3088: a ragged last tile of 16 columns
+    hbq = torch.randn(H, device=DEV)
+    rope = torch.randn(200, 32, 2, device=DEV)
+    res = {}
+    before = knob.value
+    for pair in (0, 1):
+        knob.value = pair
+        try:
+            out = resid.clone()
+            outb = torch.zeros(M, C, device=DEV, dtype=torch.bfloat16)
+            ss = torch.zeros(C // 128, M, device=DEV)
+            gemm(M, C, K, [a], w, _lib.EPI_RESID, out=out, ldo=C, resid=out, ldr=C, gate=gate, gate_bstride=0, bias=bias, out_b16=outb, ldo_b16=C,
+                 row_ss=ss, row_ss_ld=M)
+            v1 = list(variant)
+            og = torch.zeros(M, inner, device=DEV, dtype=torch.bfloat16)
+            gemm(M, 2 * inner, K, [a], wg, _lib.EPI_GEGLU, out=og, ldo=inner, bias=bg)
+            v2 = list(variant)
+            qk = torch.zeros(M, 2 * HD, device=DEV, dtype=torch.bfloat16)
+            vr = torch.zeros(M, HD, device=DEV, dtype=torch.bfloat16)
+            hg = torch.zeros(M, H, device=DEV)
+            gemm(M, 3 * HD + H, K, [a], wq, _lib.EPI_QKV, out=qk, ldo=2 * HD, q_end=HD, k_end=2 * HD, v_end=3 * HD, q_scale=0.125, rope=rope,
+                 pos_off=0, rows_per_batch=200, vt=vr, vt_ld=HD, heads_v=H, hgate=hg, hgate_ld=H, hgate_bias=hbq, v_rowmajor=1)
+            v3 = list(variant)
+            of = torch.zeros(M, C, device=DEV)
+            gemm(M, C, K, [a], w, _lib.EPI_F32, out=of, ldo=C, bias=bias)
+            v4 = list(variant)
+        finally:
+            knob.value = before
+        assert v1 == [5, 256, 8 if K <= 3072 else 4, 2 if pair else 1] and v2 == [_lib.EPI_GEGLU, 256, 8 if K <= 1536 else 4, 2 if pair else 1], (v1, v2)
+        assert v3[0] == _lib.EPI_QKV and v3[3] == (2 if pair else 1) and v4[0] == _lib.EPI_F32 and v4[3] == (2 if pair else 1), (v3, v4)
+        res[pair] = (out, outb, ss, og, qk, vr, hg, of)
+    ref = resid + (a.float() @ w.float().t() + bias) * gate
+    assert rel(res[1][0], ref) < 1e-5
+    assert rel(res[1][6], torch.sigmoid((a.float() @ wq.float().t())[:, 3 * HD:] + hbq)) < 1e-4      # the ragged tile's columns
+    for x, y in zip(res[0], res[1]):
+        assert torch.equal(x, y)
+
+
 def test_resid_row_sums_do_not_depend_on_the_tiling():
     """The same rows give bit-identical row-sum partials and results whether the launch takes 128-wide tiles (few rows) or 256-wide
     tiles with 8 or 4 epilogue warps (many rows): a clip's latent must not depend on the batch it is sampled in."""

@@ -10,6 +10,7 @@ from gpu_util import gemm, DEV
 M = 100096
 knob = C.c_int.in_dll(_lib.lib(), 'e2b_gemm_prefetch_kb')
 rt_knob = C.c_int.in_dll(_lib.lib(), 'e2b_gemm_resid_tma')
+pair_knob = C.c_int.in_dll(_lib.lib(), 'e2b_gemm_cta_pair')
 MODE = os.environ.get('AB', 'resid')        # 'pf': A-operand prefetch distances; 'resid': TMA vs classic residual epilogue
 flush = torch.empty(256 * 1024 * 1024, device=DEV)
 
@@ -38,6 +39,13 @@ def case(name, N, srcs, epi, mk):
             us = timeit(N, K, epi, mk(), srcs)
             row += f'  pf={pf:2d} {us:7.1f} us ({2 * M * N * K / us / 1e6:5.0f} TF/s)'
         knob.value = 0
+    elif MODE == 'pair':
+        ex = mk()
+        for pr in (0, 1):
+            pair_knob.value = pr
+            us = timeit(N, K, epi, ex, srcs)
+            row += f'  {"CTA pair" if pr else "1 CTA   "} {us:7.1f} us ({2 * M * N * K / us / 1e6:5.0f} TF/s)'
+        pair_knob.value = 0
     else:
         ex = mk()
         nbytes = 2.0 * M * K + (8.0 * M * N if epi == _lib.EPI_RESID else 0) + (2.0 * M * N if 'out_b16' in ex else 0)

@@ -41,12 +41,15 @@ struct GemmArgs {
 // EW = number of epilogue warps.  4: one per TMEM lane quarter, 4-stage operand ring (large K, MMA-bound).  8: two per
 // quarter taking alternate 32-column chunks, 3-stage ring: for K <= 1024 the epilogue (one warp per scheduler, IPC ~0.3)
 // is longer than the 8K-cycle mainloop of a tile, so thread-level parallelism in the epilogue is worth a pipeline stage.
-template <int BN, int EW, int EPI = 0>
+// CG = 2: a CTA PAIR (cluster of two CTAs on the SMs of one TPC) works on one 256 x BN tile with tcgen05.mma.cta_group::2: each CTA
+// stages its own 128 rows of A and HALF of the B tile (BN / 2 rows of W), the pair's tensor cores read both halves -- a third less
+// L2 -> shared-memory traffic per FLOP and two thirds of the shared-memory operand reads of two independent 128 x BN tiles.
+template <int BN, int EW, int EPI = 0, int CG = 1>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? (EW == 8 ? 3 : 4) : 6;
+  static constexpr int STAGES = CG == 2 ? ((EPI == EPI_RESID_TMA && EW == 8) ? 4 : (EW == 8 ? 5 : 6)) : ((BN == 256) ? (EW == 8 ? 3 : 4) : 6);
   static constexpr int THREADS = 128 + 32 * EW;
   // EPI_RESID_TMA: per epilogue warp RT_NBUF residual / result tiles of 32 x 32 fp32 (4 KB, SWIZZLE_128B) and one 32 x 32 bf16
   // tile (2 KB, SWIZZLE_64B); then the gate and bias vectors of the current column tile (2 x BN floats)
@@ -162,10 +165,21 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory"); }
 
-template <int BN, int EW>
+// How a CTA walks the output tiles: tile index t0, t0 + tstep, ... < total; tile -> first row (tile / n_tiles) * mrows + moff.
+// One CTA per tile: mrows = 128, moff = 0; a CTA pair: both CTAs walk the pair's 256-row tiles, moff = 128 * rank.
+struct TileWalk { int t0, tstep, total, n_tiles, mrows, moff; bool remote_tempty; };
+__device__ __forceinline__ int tile_m0(const TileWalk& w, int tile) { return (tile / w.n_tiles) * w.mrows + w.moff; }
+// epilogue warp done with a TMEM accumulator buffer: tell the MMA issuer (in a CTA pair it lives in the leader CTA)
+__device__ __forceinline__ void arrive_tempty(const TileWalk& w, uint64_t* bar) {
+  if (w.remote_tempty) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(smem_u32(bar) & 0xFEFFFFFFu) : "memory");
+  else mbar_arrive(bar);
+}
+
+template <int BN, int EW, int CG>
 __device__ __forceinline__ void rt_epilogue(const GemmArgs& args, uint8_t* sEpi, uint64_t* rfull_all, uint64_t* tfull, uint64_t* tempty,
-                                            uint32_t tmem_base, int warp, int lane, int total, int n_tiles) {
-  using Cfg = GemmCfg<BN, EW, EPI_RESID_TMA>;
+                                            uint32_t tmem_base, int warp, int lane, const TileWalk tw) {
+  using Cfg = GemmCfg<BN, EW, EPI_RESID_TMA, CG>;
+  const int total = tw.total, n_tiles = tw.n_tiles;
   constexpr int NBUF = Cfg::RT_NBUF;
   constexpr int CSTEP = EW / 4;
   const e2b_gemm_desc& d = args.d;
@@ -187,14 +201,14 @@ __device__ __forceinline__ void rt_epilogue(const GemmArgs& args, uint8_t* sEpi,
 
   // running chunk sequence of this warp over all its tiles: chunk q lives in buffer q % NBUF, barrier phase (q / NBUF) & 1
   int q_issue = 0, q_use = 0;
-  int it_tile = blockIdx.x, it_c = c_first;     // cursor of the next residual chunk to request
+  int it_tile = tw.t0, it_c = c_first;          // cursor of the next residual chunk to request
   auto cursor_ok = [&]() { return it_tile < total; };
   // (it_tile, it_c) -> the next chunk this warp really has: column chunks past the width of a ragged last tile do not exist
   auto cursor_normalize = [&]() {
     while (it_tile < total) {
       if (it_c < c_first + CPW && (it_tile % n_tiles) * BN + it_c * 32 < d.N) break;
       it_c = c_first;
-      it_tile += gridDim.x;
+      it_tile += tw.tstep;
       if (it_tile < total && (it_tile % n_tiles) * BN + c_first * 32 >= d.N) it_c = c_first + CPW;   // not even the first chunk: skip the tile
     }
   };
@@ -203,7 +217,7 @@ __device__ __forceinline__ void rt_epilogue(const GemmArgs& args, uint8_t* sEpi,
     cursor_normalize();
   };
   auto issue_load = [&]() {                     // lane 0 only
-    const int m0 = (it_tile / n_tiles) * BM, n0 = (it_tile % n_tiles) * BN;
+    const int m0 = tile_m0(tw, it_tile), n0 = (it_tile % n_tiles) * BN;
     const int b = q_issue % NBUF;
     mbar_arrive_expect_tx(&rfull[b], 4096);
     tma_load_2d(rbuf + b * 4096, &args.tmR, &rfull[b], n0 + it_c * 32, m0 + ew * 32);
@@ -216,10 +230,10 @@ __device__ __forceinline__ void rt_epilogue(const GemmArgs& args, uint8_t* sEpi,
   }
 
   int it = 0;
-  for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+  for (int tile = tw.t0; tile < total; tile += tw.tstep, ++it) {
     const int as = it & 1;
     const uint32_t aphase = (it >> 1) & 1;
-    const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+    const int m0 = tile_m0(tw, tile), n0 = (tile % n_tiles) * BN;
     const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * BN;
     const int ncols = min(BN, d.N - n0);
     const int row = m0 + ew * 32 + lane;
@@ -314,15 +328,15 @@ __device__ __forceinline__ void rt_epilogue(const GemmArgs& args, uint8_t* sEpi,
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tempty[as]);
+    if (lane == 0) arrive_tempty(tw, &tempty[as]);
   }
   if (lane == 0) bulk_wait0();                  // every store of this lane has landed before the CTA may exit
   __syncwarp();
 }
 
-template <int BN, int EPI, int EW>
+template <int BN, int EPI, int EW, int CG = 1>
 __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_constant__ GemmArgs args) {
-  using Cfg = GemmCfg<BN, EW, EPI>;
+  using Cfg = GemmCfg<BN, EW, EPI, CG>;
   // Used directly (no integer round-trip) so the compiler keeps the shared address space: the earlier manual 1024-byte
   // round-up through uintptr_t turned every access into generic LD.E/ST.E.  SWIZZLE_128B needs a 1024-byte aligned base;
   // with no static shared memory the dynamic window starts at offset 0 -- checked once below.
@@ -346,8 +360,17 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (d.M + BM - 1) / BM;
   const int n_tiles = (d.N + BN - 1) / BN;
-  const int total = m_tiles * n_tiles;
   const int KB = d.K / BK;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;     // CTA pair: 0 = leader (issues the MMAs), 1 = follower
+  TileWalk tw;
+  tw.n_tiles = n_tiles;
+  tw.t0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  tw.tstep = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  tw.total = CG == 2 ? ((m_tiles + 1) / 2) * n_tiles : m_tiles * n_tiles;
+  tw.mrows = BM * CG;
+  tw.moff = (int)rank * BM;
+  tw.remote_tempty = CG == 2 && rank != 0;
+  const int total = tw.total;
 
   // Warp roles: 0..EW-1 epilogue, EW = TMA producer, EW+1 = MMA issuer, EW+2 = TMEM allocator.  The single-thread issuers
   // take the highest warp ids because the scheduler arbitrates highest-warp-id-first: as warps 0/1 they were starved by the
@@ -370,18 +393,19 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], EW);
+      mbar_init(&tempty[s], EW * CG);       // CTA pair: the epilogue warps of BOTH CTAs release the leader's accumulator buffer
     }
     if constexpr (EPI == EPI_RESID_TMA)
       for (int s = 0; s < 2 * EW; ++s) mbar_init(&rfull[s], 1);
     fence_mbar_init();
   }
   if (warp == W_ALLOC) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG == 2) { tmem_alloc_cg2(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_cg2(); }
+    else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync();          // the peer's barriers are initialised before anything is signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -398,48 +422,57 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
     // (tools/bench_gemm_pf.py, profiles/r02_gemm_prefetch_ab.txt: GEGLU text 1385 -> 1197 TF/s, FF2 audio 1125 -> 950, out-projections
     // unchanged) and 1.6-1.9x the algorithmic DRAM reads under ncu -- the operand ring already covers the latency, the extra requests
     // only compete with the real loads.  Kept as a switch so the result can be reproduced.
-    int pf_tile = blockIdx.x, pf_k = 0, pf_src = 0, pf_k0 = 0;
+    int pf_tile = tw.t0, pf_k = 0, pf_src = 0, pf_k0 = 0;
     auto pf_step = [&]() {
       if (pf_tile >= total) return;
       if (pf_tile % n_tiles == 0 && elect_one())
-        tma_prefetch_l2_2d(&args.tmA[pf_src], (pf_k - pf_k0) * BK, (pf_tile / n_tiles) * BM);
-      if (++pf_k == KB) { pf_k = 0; pf_src = 0; pf_k0 = 0; pf_tile += gridDim.x; }
+        tma_prefetch_l2_2d(&args.tmA[pf_src], (pf_k - pf_k0) * BK, tile_m0(tw, pf_tile));
+      if (++pf_k == KB) { pf_k = 0; pf_src = 0; pf_k0 = 0; pf_tile += tw.tstep; }
       else while (pf_k >= args.kb_end[pf_src]) { pf_k0 = args.kb_end[pf_src]; ++pf_src; }
     };
     if (args.pf_kb > 0)
       for (int i = 0; i < args.pf_kb; ++i) pf_step();
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    for (int tile = tw.t0; tile < total; tile += tw.tstep) {
       const int n_tile = tile % n_tiles;
-      const int m0 = (tile / n_tiles) * BM, n0 = n_tile * BN;
+      const int m0 = tile_m0(tw, tile), n0 = n_tile * BN;
       const bool tail = args.tail_rows > 0 && n_tile == n_tiles - 1;
       const CUtensorMap* tmb = tail ? &args.tmBt : &args.tmB;
-      const uint32_t bytes = tail ? (uint32_t)(Cfg::A_BYTES + args.tail_rows * BK * 2) : (uint32_t)Cfg::STAGE_BYTES;
+      // bytes this CTA stages per K block; rows of W it owns in the tile (a CTA pair splits the tile's columns in halves)
+      const int brows = tail ? args.tail_rows / CG : BN / CG;
+      const uint32_t bytes = (uint32_t)(Cfg::A_BYTES + brows * BK * 2);
       int src = 0, kb0 = 0;
       for (int kb = 0; kb < KB; ++kb) {
         while (kb >= args.kb_end[src]) { kb0 = args.kb_end[src]; ++src; }
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[stage], bytes);
-          tma_load_2d(sA + stage * Cfg::A_BYTES, &args.tmA[src], &full[stage], (kb - kb0) * BK, m0);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, tmb, &full[stage], kb * BK, n0);
+          if constexpr (CG == 2) {
+            // both CTAs load their halves and signal the LEADER's barrier, which expects the bytes of the pair
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * bytes);
+            tma_load_2d_cg2(sA + stage * Cfg::A_BYTES, &args.tmA[src], &full[stage], (kb - kb0) * BK, m0);
+            tma_load_2d_cg2(sB + stage * Cfg::B_BYTES, tmb, &full[stage], kb * BK, n0 + (int)rank * brows);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], bytes);
+            tma_load_2d(sA + stage * Cfg::A_BYTES, &args.tmA[src], &full[stage], (kb - kb0) * BK, m0);
+            tma_load_2d(sB + stage * Cfg::B_BYTES, tmb, &full[stage], kb * BK, n0);
+          }
         }
         __syncwarp();
         if (args.pf_kb > 0) pf_step();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == W_MMA) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == W_MMA && rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (CTA pair: the leader issues for both CTAs)
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+    for (int tile = tw.t0; tile < total; tile += tw.tstep, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       // A ragged last column tile (QKV + head-gate: N = 3088 = 12 x 256 + 16) only multiplies the columns it has, rounded up to the
       // MMA's N granularity of 16: a 16-column tile costs 1/16 of the tensor time instead of a full tile (8 % of the QKV GEMMs)
       const int nv = min(BN, d.N - (tile % n_tiles) * BN);
-      const uint32_t idesc = umma_idesc_bf16(BM, (uint32_t)((nv + 15) & ~15));
+      const uint32_t idesc = umma_idesc_bf16(BM * CG, (uint32_t)((nv + 16 * CG - 1) & ~(16 * CG - 1)));   // 16 columns per CTA
       mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN;
@@ -449,11 +482,19 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
         if (elect_one()) {
           const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
           const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
+          if constexpr (CG == 2) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_ss(tmem_d, da + k * UMMA_K_STEP_ENC, db + k * UMMA_K_STEP_ENC, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);
-          if (kb == KB - 1) umma_commit(&tfull[as]);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_ss_cg2(tmem_d, da + k * UMMA_K_STEP_ENC, db + k * UMMA_K_STEP_ENC, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_cg2(&empty[stage]);         // frees the slot in both CTAs
+            if (kb == KB - 1) umma_commit_cg2(&tfull[as]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_ss(tmem_d, da + k * UMMA_K_STEP_ENC, db + k * UMMA_K_STEP_ENC, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty[stage]);
+            if (kb == KB - 1) umma_commit(&tfull[as]);
+          }
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -461,7 +502,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
     }
   } else if (warp < EW) {
    if constexpr (EPI == EPI_RESID_TMA) {
-    rt_epilogue<BN, EW>(args, sEpi, rfull, tfull, tempty, tmem_base, warp, lane, total, n_tiles);
+    rt_epilogue<BN, EW, CG>(args, sEpi, rfull, tfull, tempty, tmem_base, warp, lane, tw);
    } else {
     // ------------------------------------------------------------ epilogue (TMEM -> regs -> smem transpose -> global)
     const int ewi = warp;
@@ -475,10 +516,10 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
     const float4* bufr = buf + rsub * EPI_PITCH4 + cg;          // + 4k * EPI_PITCH4 selects row 4k + rsub
     const bool per_batch_gate = (EPI == E2B_EPI_RESID) && d.gate && d.gate_bstride != 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+    for (int tile = tw.t0; tile < total; tile += tw.tstep, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      const int m0 = tile_m0(tw, tile), n0 = (tile % n_tiles) * BN;
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * BN;
       const int ncols = min(BN, d.N - n0);                      // valid packed columns of this tile (multiple of 4)
       EpiRows R;
@@ -518,9 +559,9 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
       if constexpr (EPI == E2B_EPI_RESID) {
         // Pull the residual block of this CTA's NEXT tile towards L2 now, a whole epilogue ahead: the epilogue's residual loads
         // were DRAM misses with only ~32 KB in flight per SM (tools/bench_gemm3.py: out-projections 6-10 % faster with it).
-        const int nt = tile + gridDim.x;
+        const int nt = tile + tw.tstep;
         if (nt < total) {
-          const int pm = (nt / n_tiles) * BM + ew * 32 + lane, pn = (nt % n_tiles) * BN;
+          const int pm = tile_m0(tw, nt) + ew * 32 + lane, pn = (nt % n_tiles) * BN;
           if (pm < d.M) {
             const float* src = d.resid + (size_t)pm * d.ldr + pn;
 #pragma unroll
@@ -749,14 +790,18 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);     // one arrival per epilogue warp
+      if (lane == 0) arrive_tempty(tw, &tempty[as]);     // one arrival per epilogue warp
     }
    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == W_ALLOC) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if constexpr (CG == 2) cluster_sync();          // neither CTA leaves while the pair's MMAs / remote arrivals may still touch it
+  if (warp == W_ALLOC) {
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -769,8 +814,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 }  // namespace e2b
-// internal epilogue id, column tile width and epilogue warps of the most recent launch (tests assert which variant ran)
-extern "C" { int e2b_gemm_last_variant[3] = {-1, 0, 0}; }
+// internal epilogue id, column tile width, epilogue warps and CTAs per tile of the most recent launch (tests assert which variant ran)
+extern "C" { int e2b_gemm_last_variant[4] = {-1, 0, 0, 0}; }
 namespace e2b {
 
 static PFN_encodeTiled get_encode() {
@@ -836,25 +881,47 @@ int make_tmap_generic(CUtensorMap* m, CUtensorMapDataType dt, int rank, const vo
 
 static int num_sms() { return e2b_num_sms(); }
 
-template <int BN, int EPI, int EW>
+template <int BN, int EPI, int EW, int CG = 1>
 static int launch_t(const GemmArgs& a, cudaStream_t st) {
-  using Cfg = GemmCfg<BN, EW, EPI>;
+  using Cfg = GemmCfg<BN, EW, EPI, CG>;
   static bool configured[E2B_MAX_DEVICES] = {false};
   bool& conf = configured[e2b_device_slot()];
   if (!conf) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, EPI, EW, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { e2b_set_kernel_error("gemm smem attribute: %s", cudaGetErrorString(e)); return -1; }
     conf = true;
   }
-  const int tiles = ((a.d.M + BM - 1) / BM) * ((a.d.N + BN - 1) / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int m_tiles = (a.d.M + BM - 1) / BM, n_tiles = (a.d.N + BN - 1) / BN;
+  int grid;
+  if (CG == 2) {                                   // one cluster of two CTAs per 256-row tile
+    const int pairs = ((m_tiles + 1) / 2) * n_tiles;
+    grid = 2 * (pairs < num_sms() / 2 ? pairs : num_sms() / 2);
+  } else {
+    const int tiles = m_tiles * n_tiles;
+    grid = tiles < num_sms() ? tiles : num_sms();
+  }
   static const char* kinds[] = {"gemm_bf16", "gemm_f32", "gemm_geglu", "gemm_resid", "gemm_qkv", "gemm_resid"};
   const double out_cols = (EPI == E2B_EPI_GEGLU) ? a.d.N / 2.0 : a.d.N;
   const double out_bytes = (EPI == E2B_EPI_F32) ? 4.0 : ((EPI == E2B_EPI_RESID || EPI == EPI_RESID_TMA) ? 8.0 : 2.0);
   ProfScope ps(st, kinds[EPI], a.d.M, a.d.N, a.d.K, 2.0 * a.d.M * a.d.N * a.d.K,
                2.0 * ((double)a.d.M * a.d.K + (double)a.d.N * a.d.K) + out_bytes * a.d.M * out_cols + (a.d.out_b16 ? 2.0 * a.d.M * out_cols : 0.0));
-  e2b_gemm_last_variant[0] = EPI; e2b_gemm_last_variant[1] = BN; e2b_gemm_last_variant[2] = EW;
-  gemm_kernel<BN, EPI, EW><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
+  e2b_gemm_last_variant[0] = EPI; e2b_gemm_last_variant[1] = BN; e2b_gemm_last_variant[2] = EW; e2b_gemm_last_variant[3] = CG;
+  if (CG == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, EW, CG>, a);
+    if (e != cudaSuccess) { e2b_set_kernel_error("gemm cluster launch: %s", cudaGetErrorString(e)); return -1; }
+    return 0;
+  }
+  gemm_kernel<BN, EPI, EW, CG><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { e2b_set_kernel_error("gemm launch: %s", cudaGetErrorString(e)); return -1; }
   return 0;
@@ -878,6 +945,10 @@ extern "C" const char* e2b_kernel_last_error(void) { return g_err; }
 extern "C" int e2b_gemm_resid_tma = -1;
 
 extern "C" int e2b_gemm_resid_tma_ew8_max_k = 3072;
+// CTA-pair (tcgen05 cta_group::2, 256-row tiles) variants for launches with 256-wide column tiles whose tile count fills the 74
+// clusters (E2B_GEMM_CG2=0 switches them off).  tools/bench_gemm_pf.py (AB=pair), profiles/r02_gemm_cta_pair_ab.txt: +8-12 % on the
+// large GEMMs standalone (GEGLU text 1365 -> 1516 TF/s), 122.9 -> 128.4 audio-s/s for the whole C2 step.
+extern "C" int e2b_gemm_cta_pair = -1;
 // A-operand L2 prefetch distance in K blocks of 64 (0 = off); settable for A/B tests (E2B_GEMM_PF)
 extern "C" int e2b_gemm_prefetch_kb = -1;
 extern "C" int e2b_gemm_ew8_max_k = 1536;   // tools/bench_gemm3.py: 8 warps win up to K=1280, tie at 2048, lose at 5120
@@ -902,6 +973,10 @@ static void read_env_knobs() {
   if (e2b_gemm_prefetch_kb < 0) {
     const char* e = getenv("E2B_GEMM_PF");
     e2b_gemm_prefetch_kb = e ? atoi(e) : 0;
+  }
+  if (e2b_gemm_cta_pair < 0) {
+    const char* e = getenv("E2B_GEMM_CG2");
+    e2b_gemm_cta_pair = e ? atoi(e) : 1;
   }
   static bool once = false;
   if (!once) {
@@ -952,11 +1027,17 @@ extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
   }
   read_env_knobs();
   a.pf_kb = e2b_gemm_prefetch_kb;
-  if (make_tmap_bf16(&a.tmB, d->w, d->N, d->K, d->ldw, bn256 ? 256 : 128)) return -1;
+  // CTA pair: N a multiple of 256 (no ragged tile), enough 256-row tiles to fill 74 clusters, GEGLU or the TMA residual epilogue
+  // CTA pair (256-row tiles, tcgen05 cta_group::2): 256-wide column tiles and enough tiles to fill the 74 clusters; every epilogue
+  // except the classic residual one (only reached with unaligned buffers or the fp32 mode's hi/lo copies)
+  const bool pair = e2b_gemm_cta_pair && bn256 && (long long)((d->M + 255) / 256) * ((d->N + 255) / 256) >= e2b_num_sms() / 2 &&
+                    (d->epi != E2B_EPI_RESID || e2b_gemm_resid_uses_tma(d));
+  if (make_tmap_bf16(&a.tmB, d->w, d->N, d->K, d->ldw, pair ? 128 : (bn256 ? 256 : 128))) return -1;
   {
-    const int bn = bn256 ? 256 : 128, rem = d->N % bn, rows16 = (rem + 15) / 16 * 16;
-    a.tail_rows = (rem > 0 && rows16 < bn) ? rows16 : 0;
-    if (a.tail_rows && make_tmap_bf16(&a.tmBt, d->w, d->N, d->K, d->ldw, (uint32_t)a.tail_rows)) return -1;
+    // ragged last column tile: its own B box; the MMA takes N in steps of 16 per CTA, a pair splits the rounded-up tile in halves
+    const int bn = bn256 ? 256 : 128, rem = d->N % bn, gran = pair ? 32 : 16, rows = (rem + gran - 1) / gran * gran;
+    a.tail_rows = (rem > 0 && rows < bn) ? rows : 0;
+    if (a.tail_rows && make_tmap_bf16(&a.tmBt, d->w, d->N, d->K, d->ldw, (uint32_t)(pair ? a.tail_rows / 2 : a.tail_rows))) return -1;
   }
 #define E2B_DISPATCH(BN_, EW_)                                                        \
   switch (d->epi) {                                                                   \
@@ -964,6 +1045,13 @@ extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
     case E2B_EPI_F32: return launch_t<BN_, E2B_EPI_F32, EW_>(a, stream);              \
     case E2B_EPI_RESID: return launch_t<BN_, E2B_EPI_RESID, EW_>(a, stream);          \
     case E2B_EPI_QKV: return launch_t<BN_, E2B_EPI_QKV, EW_>(a, stream);              \
+    default: break;                                                                   \
+  }
+#define E2B_DISPATCH_PAIR(EW_)                                                        \
+  switch (d->epi) {                                                                   \
+    case E2B_EPI_BF16: return launch_t<256, E2B_EPI_BF16, EW_, 2>(a, stream);         \
+    case E2B_EPI_F32: return launch_t<256, E2B_EPI_F32, EW_, 2>(a, stream);           \
+    case E2B_EPI_QKV: return launch_t<256, E2B_EPI_QKV, EW_, 2>(a, stream);           \
     default: break;                                                                   \
   }
   if (e2b_gemm_resid_uses_tma(d)) {
@@ -975,6 +1063,7 @@ extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
     if (make_tmap_swizzled(&a.tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d->out, dims, so, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
     if (d->out_b16 && make_tmap_swizzled(&a.tmO16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d->out_b16, dims, sh, box, CU_TENSOR_MAP_SWIZZLE_64B)) return -1;
     if (!bn256) return launch_t<128, EPI_RESID_TMA, 4>(a, stream);
+    if (pair) return d->K <= e2b_gemm_resid_tma_ew8_max_k ? launch_t<256, EPI_RESID_TMA, 8, 2>(a, stream) : launch_t<256, EPI_RESID_TMA, 4, 2>(a, stream);
     if (d->K <= e2b_gemm_resid_tma_ew8_max_k) return launch_t<256, EPI_RESID_TMA, 8>(a, stream);
     return launch_t<256, EPI_RESID_TMA, 4>(a, stream);
   }
@@ -985,12 +1074,15 @@ extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
   if (d->row_ss || d->b16_scale) { e2b_set_kernel_error("gemm: row sums / scaled bf16 copy need the TMA residual epilogue (EPI_RESID, 16-byte aligned buffers, no hi/lo split)"); return -1; }
   const bool ew8 = d->K <= e2b_gemm_ew8_max_k;   // small K: epilogue-bound, use 8 epilogue warps + 3 stages
   if (bn256) {
+    if (d->epi == E2B_EPI_GEGLU && pair) return ew8 ? launch_t<256, E2B_EPI_GEGLU, 8, 2>(a, stream) : launch_t<256, E2B_EPI_GEGLU, 4, 2>(a, stream);
     if (d->epi == E2B_EPI_GEGLU) return ew8 ? launch_t<256, E2B_EPI_GEGLU, 8>(a, stream) : launch_t<256, E2B_EPI_GEGLU, 4>(a, stream);
+    if (pair && d->epi != E2B_EPI_RESID) { if (ew8) { E2B_DISPATCH_PAIR(8) } else { E2B_DISPATCH_PAIR(4) } }
     if (ew8) { E2B_DISPATCH(256, 8) } else { E2B_DISPATCH(256, 4) }
   } else {
     E2B_DISPATCH(128, 4)
   }
 #undef E2B_DISPATCH
+#undef E2B_DISPATCH_PAIR
   e2b_set_kernel_error("gemm: unknown epilogue %d", d->epi);
   return -1;
 }
