@@ -44,7 +44,8 @@ def case(name, N, srcs, epi, mk):
         for pr in (0, 1):
             pair_knob.value = pr
             us = timeit(N, K, epi, ex, srcs)
-            row += f'  {"CTA pair" if pr else "1 CTA   "} {us:7.1f} us ({2 * M * N * K / us / 1e6:5.0f} TF/s)'
+            var = (C.c_int * 4).in_dll(_lib.lib(), 'e2b_gemm_last_variant')
+            row += f'  {"CTA pair" if pr else "1 CTA   "} {us:7.1f} us ({2 * M * N * K / us / 1e6:5.0f} TF/s) [epi {var[0]} bn {var[1]} ew {var[2]} cg {var[3]}]'
         pair_knob.value = 0
     else:
         ex = mk()
@@ -89,3 +90,23 @@ case('out frames', 512, [512], _lib.EPI_RESID, resid(512, False))
 case('qkv text', 3088, [1280], _lib.EPI_QKV, qkv(16))
 case('qkv audio', 3088, [1024], _lib.EPI_QKV, qkv(16))
 case('qkv frames', 1544, [512], _lib.EPI_QKV, qkv(8))
+
+if MODE == 'pair':
+    # the audio out-projection as the engine launches it: per-clip gate, bf16(x * gain) with the gain switching at a row, row sums
+    N = 1024
+    gate_b = torch.rand(128, N, device=DEV)
+    def fused(per_clip_gate, b16, scale, split, ss):
+        out = torch.randn(M, N, device=DEV)
+        ex = dict(out=out, ldo=N, resid=out, ldr=N, lens=lens, rows_per_batch=782)
+        ex.update(dict(gate=gate_b, gate_bstride=N) if per_clip_gate else dict(gate=torch.rand(N, device=DEV), gate_bstride=0))
+        if b16: ex.update(out_b16=torch.empty(M, N, device=DEV, dtype=torch.bfloat16), ldo_b16=N)
+        if scale: ex.update(b16_scale=torch.rand(N, device=DEV))
+        if split: ex.update(b16_scale2=torch.rand(N, device=DEV), b16_split_row=M // 2)
+        if ss: ex.update(row_ss=torch.empty(16, M, device=DEV), row_ss_ld=M)
+        return lambda: ex
+    case('out audio +clip gate', N, [1024], _lib.EPI_RESID, fused(1, 0, 0, 0, 0))
+    case('out audio +bf16', N, [1024], _lib.EPI_RESID, fused(1, 1, 0, 0, 0))
+    case('out audio +gain', N, [1024], _lib.EPI_RESID, fused(1, 1, 1, 0, 0))
+    case('out audio +split', N, [1024], _lib.EPI_RESID, fused(1, 1, 1, 1, 0))
+    case('out audio +row sums', N, [1024], _lib.EPI_RESID, fused(1, 1, 1, 1, 1))
+    case('out audio sums only', N, [1024], _lib.EPI_RESID, fused(1, 1, 0, 0, 1))

@@ -1027,7 +1027,6 @@ extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
   }
   read_env_knobs();
   a.pf_kb = e2b_gemm_prefetch_kb;
-  // CTA pair: N a multiple of 256 (no ragged tile), enough 256-row tiles to fill 74 clusters, GEGLU or the TMA residual epilogue
   // CTA pair (256-row tiles, tcgen05 cta_group::2): 256-wide column tiles and enough tiles to fill the 74 clusters; every epilogue
   // except the classic residual one (only reached with unaligned buffers or the fp32 mode's hi/lo copies)
   const bool pair = e2b_gemm_cta_pair && bn256 && (long long)((d->M + 255) / 256) * ((d->N + 255) / 256) >= e2b_num_sms() / 2 &&
