@@ -266,13 +266,67 @@ def test_cta_pair_variants_match_single_cta(K, ew):
         finally:
             knob.value = before
         assert v1 == [5, 256, 8 if K <= 3072 else 4, 2 if pair else 1] and v2 == [_lib.EPI_GEGLU, 256, 8 if K <= 1536 else 4, 2 if pair else 1], (v1, v2)
-        assert v3[0] == _lib.EPI_QKV and v3[3] == (2 if pair else 1) and v4[0] == _lib.EPI_F32 and v4[3] == (2 if pair else 1), (v3, v4)
+        assert v3[0] == 6 and v3[3] == (2 if pair else 1) and v4[0] == _lib.EPI_F32 and v4[3] == (2 if pair else 1), (v3, v4)
         res[pair] = (out, outb, ss, og, qk, vr, hg, of)
     ref = resid + (a.float() @ w.float().t() + bias) * gate
     assert rel(res[1][0], ref) < 1e-5
     assert rel(res[1][6], torch.sigmoid((a.float() @ wq.float().t())[:, 3 * HD:] + hbq)) < 1e-4      # the ragged tile's columns
     for x, y in zip(res[0], res[1]):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize('B,H,K,cross,scaled', [(40, 16, 1024, 0, 1), (40, 8, 512, 0, 0), (3, 16, 1024, 0, 1), (40, 16, 1024, 1, 1), (17, 16, 2048, 0, 0), (17, 4, 1024, 0, 1)])
+def test_qkv_tma_store_epilogue_matches_classic(B, H, K, cross, scaled):
+    """The row-per-lane / TMA-store QKV epilogue (internal id 6: rope values of a lane's row kept in registers, bf16 tiles leave by
+    TMA) against the classic transpose epilogue: bit-identical q | k, V rows and head gates -- for 256-wide tiles with 8 and 4
+    epilogue warps, CTA pairs, the 128-wide tiles of a few-row launch, a q-only (cross-attention) projection, with and without the
+    norm row scale; rows past M and the columns past N of the ragged tile must stay untouched."""
+    knob = ctypes.c_int.in_dll(_lib.lib(), 'e2b_gemm_qkv_tma')
+    variant = (ctypes.c_int * 4).in_dll(_lib.lib(), 'e2b_gemm_last_variant')
+    Nseq = 203
+    M, HD = B * Nseq, H * 64
+    g = torch.Generator(device='cpu').manual_seed(B * 1000 + H)
+    a = bf(torch.randn(M, K, generator=g)).to(DEV)
+    N = (HD if cross else 3 * HD) + H
+    w = bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    hb = torch.randn(H, generator=g).to(DEV)
+    ang = (torch.arange(Nseq + 5).float()[:, None] * (1. / (10000 ** (torch.arange(0, 64, 2).float() / 64)))[None, :])
+    rope = torch.stack((ang.cos(), ang.sin()), -1).to(DEV).contiguous()
+    ss = (torch.rand(3, M, generator=g) * K / 3).to(DEV)
+    extra = dict(in_row_ss=ss, in_row_parts=3, in_row_ss_ld=M, in_row_mult=math.sqrt(K)) if scaled else {}
+    qcols = HD if cross else 2 * HD
+    res = {}
+    before = knob.value
+    for tma in (0, 1):
+        knob.value = tma
+        try:
+            qk = torch.full((M + 3, qcols), 7.0, device=DEV, dtype=torch.bfloat16)
+            vr = torch.full((M + 3, HD), 7.0, device=DEV, dtype=torch.bfloat16)
+            hg = torch.full((M + 3, H), 7.0, device=DEV)
+            gemm(M, N, K, [a], w, _lib.EPI_QKV, out=qk, ldo=qcols, q_end=HD, k_end=qcols, v_end=qcols if cross else 3 * HD, q_scale=0.125,
+                 rope=rope, pos_off=5, rows_per_batch=Nseq, vt=vr, vt_ld=HD, heads_v=H, hgate=hg, hgate_ld=H, hgate_bias=hb, v_rowmajor=1, **extra)
+            v = list(variant)
+        finally:
+            knob.value = before
+        assert v[0] == (6 if tma else _lib.EPI_QKV), v
+        if tma:
+            bn = 128 if (B == 3 or H == 4) else 256                      # few rows / N = 772: 128-wide tiles
+            assert v[1] == bn and v[2] == (4 if (K > 1536 or bn == 128) else 8), v
+        res[tma] = (qk, vr, hg)
+    for x, y in zip(res[0], res[1]):
+        assert torch.equal(x, y)
+    assert (res[1][0][M:] == 7.0).all() and (res[1][1][M:] == 7.0).all() and (res[1][2][M:] == 7.0).all()
+    full = a.float() @ w.float().t()
+    if scaled:
+        full = full * (math.sqrt(K) / ss.sum(0).sqrt())[:, None]
+    assert rel(res[1][2][:M], torch.sigmoid(full[:, N - H:] + hb)) < 1e-4
+    if not cross:
+        assert rel(res[1][1][:M], full[:, 2 * HD:3 * HD]) < 5e-3
+    t = full[:, :qcols].reshape(B, Nseq, qcols // 64, 32, 2)
+    c, sn = rope[None, 5:5 + Nseq, None, :, 0], rope[None, 5:5 + Nseq, None, :, 1]
+    rot = torch.stack((t[..., 0] * c - t[..., 1] * sn, t[..., 1] * c + t[..., 0] * sn), -1).reshape(M, qcols)
+    rot[:, :HD] *= 0.125
+    assert rel(res[1][0][:M], rot) < 5e-3
 
 
 def test_resid_row_sums_do_not_depend_on_the_tiling():

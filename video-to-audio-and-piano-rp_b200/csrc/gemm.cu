@@ -26,11 +26,14 @@ constexpr int BK = 64;
 
 // Internal epilogue id: E2B_EPI_RESID with the residual stream moved by the TMA unit (see rt_epilogue below).
 constexpr int EPI_RESID_TMA = 5;
+// Internal epilogue id: E2B_EPI_QKV (bf16 mode, V as rows) with row-per-lane arithmetic and TMA stores (see qt_epilogue below).
+constexpr int EPI_QKV_TMA = 6;
 
 struct GemmArgs {
   CUtensorMap tmA[E2B_MAX_SRC];
   CUtensorMap tmB;
   CUtensorMap tmR, tmO, tmO16;   // EPI_RESID_TMA: fp32 residual in, fp32 result out, bf16 copy out (boxes of 32 rows x 32 columns)
+                                 // EPI_QKV_TMA: tmO = q | k rows [M, k_end], tmO16 = v rows [M, v_end - k_end] (bf16, 32 x 32 boxes)
   CUtensorMap tmBt;          // ragged last column tile: the same W with a box of tail_rows rows (no zero-filled rows through the pipe)
   int tail_rows;             // 0: N is a multiple of the tile width (or the tail is a full box); else valid columns of the last tile, rounded up to 16
   int pf_kb;                 // A-operand L2 prefetch distance in 64-wide K blocks (0 = off)
@@ -56,7 +59,9 @@ struct GemmCfg {
   static constexpr bool RT = (EPI == EPI_RESID_TMA);
   static constexpr int RT_NBUF = (EW == 8) ? 2 : 1;
   static constexpr int RT_WARP_BYTES = RT_NBUF * 4096 + 2048;
-  static constexpr int EPI_BYTES = RT ? EW * RT_WARP_BYTES + 2 * BN * 4 : EW * (4608 /*epilogue transpose buffer*/ + 128 /*row scales*/);
+  // EPI_QKV_TMA: per epilogue warp two 32 x 32 bf16 tiles (2 KB each, SWIZZLE_64B) used alternately
+  static constexpr bool QT = (EPI == EPI_QKV_TMA);
+  static constexpr int EPI_BYTES = RT ? EW * RT_WARP_BYTES + 2 * BN * 4 : (QT ? EW * 4096 : EW * (4608 /*epilogue transpose buffer*/ + 128 /*row scales*/));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + (RT ? 128 : 0) /*residual-tile barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;   // 512 or 256: both powers of two
 };
@@ -334,6 +339,137 @@ __device__ __forceinline__ void rt_epilogue(const GemmArgs& args, uint8_t* sEpi,
   __syncwarp();
 }
 
+// One interleaved-RoPE pair (x-transformers rotate_half on adjacent columns) with the q pre-scale / norm row scale folded in.  Spelled
+// with explicit roundings so that the classic and the TMA-store QKV epilogues give the same bits (a clip's result must not depend
+// on which tile configuration its batch size selects).
+__device__ __forceinline__ void rope_pair(float x0, float x1, float c, float s, float sc, float& o0, float& o1) {
+  o0 = __fmul_rn(fmaf(x0, c, -__fmul_rn(x1, s)), sc);
+  o1 = __fmul_rn(fmaf(x1, c, __fmul_rn(x0, s)), sc);
+}
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// EPI_QKV_TMA: the QKV epilogue without the shared-memory transpose and without global stores from the lanes.  The classic QKV
+// epilogue issues per 32 x 32 chunk and lane 8 LDG.128 (rope), 8 STS.128 + 8 LDS.128 (transpose) and 8 STG.64 that cover only 64
+// contiguous bytes per row; with K <= 1280 that is longer than the tile's MMAs (QKV audio 1150 TF/s against 1490 for the GEGLU GEMM
+// of the same K).  Here a lane keeps the accumulator ROW tcgen05.ld gives it:
+//   * the rope (cos, sin) values of a row depend on the column only through (column % 64), and a warp that takes every second
+//     32-column chunk always sees the same half of the head: 32 values per lane, loaded ONCE per tile (before the accumulator is
+//     waited for) and kept in registers;
+//   * rotation, q pre-scale and the norm row scale are lane-local; the bf16 row goes into a 64-byte-swizzled 32 x 32 tile (two tiles
+//     per warp, used alternately) and leaves by a TMA store into the q | k buffer or the V rows; rows past M are clipped by the unit;
+//   * the head-gate columns (the ragged last tile) are stored directly: 16 floats per row.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN, int EW, int CG>
+__device__ __forceinline__ void qt_epilogue(const GemmArgs& args, uint8_t* sEpi, uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base,
+                                            int warp, int lane, const TileWalk tw) {
+  const e2b_gemm_desc& d = args.d;
+  const int ew = warp & 3;      // TMEM lane quarter
+  constexpr int HSTEP = EW / 4; // 8 warps: the two warps of a quarter take the even / the odd chunks; 4 warps: even chunks, then odd ones
+  uint8_t* hbuf = sEpi + warp * 4096;
+  const int sw3 = (lane >> 1) & 3;
+  int q = 0;                    // running chunk count of this warp: tile buffer q & 1
+  int it = 0;
+  for (int tile = tw.t0; tile < tw.total; tile += tw.tstep, ++it) {
+    const int as = it & 1;
+    const uint32_t aphase = (it >> 1) & 1;
+    const int m0 = tile_m0(tw, tile), n0 = (tile % tw.n_tiles) * BN;
+    const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * BN;
+    const int row = m0 + ew * 32 + lane;
+    const bool live = row < d.M;
+    const float* rope_row = nullptr;
+    float rs = 1.0f;
+    if (live) {
+      const int b = row / d.rows_per_batch, pos = row - b * d.rows_per_batch;
+      rope_row = d.rope + (size_t)(pos + d.pos_off) * 64;
+      if (d.in_row_ss) {      // RMSNorm of the A operand's rows as a scale of the accumulator rows (partials summed in a fixed order)
+        float s2 = 0.f;
+        for (int p = 0; p < d.in_row_parts; ++p) s2 += __ldg(d.in_row_ss + (size_t)p * d.in_row_ss_ld + row);
+        rs = d.in_row_mult / fmaxf(sqrtf(s2), 1e-12f);
+      }
+    }
+    bool waited = false;
+#pragma unroll 1
+    for (int h = (HSTEP == 2 ? (warp >> 2) : 0); h < 2; h += HSTEP) {
+      float4 rr[8];             // (cos, sin) of the 16 column pairs of this half of the head, for this lane's position
+      if (n0 + h * 32 < d.k_end) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rr[j] = live ? __ldg(reinterpret_cast<const float4*>(rope_row + h * 32) + j) : f4_zero();
+      }
+      if (!waited) {
+        mbar_wait(&tfull[as], aphase);
+        tc_fence_after();
+        waited = true;
+      }
+#pragma unroll 1
+      for (int c = h; c < BN / 32; c += 2) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= d.N) break;
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        if (col0 >= d.v_end) {                     // head-gate columns: sigmoid(acc * rs + bias), fp32, straight from the lane
+          tmem_ld_wait();
+          if (live) {
+            float* gp = d.hgate + (size_t)row * d.hgate_ld + (col0 - d.v_end);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (col0 + 4 * j < d.N) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(d.hgate_bias + (col0 - d.v_end)) + j);
+                float4 o;
+                o.x = sigmoidf_(__fadd_rn(__fmul_rn(__uint_as_float(v[4 * j + 0]), rs), bb.x));
+                o.y = sigmoidf_(__fadd_rn(__fmul_rn(__uint_as_float(v[4 * j + 1]), rs), bb.y));
+                o.z = sigmoidf_(__fadd_rn(__fmul_rn(__uint_as_float(v[4 * j + 2]), rs), bb.z));
+                o.w = sigmoidf_(__fadd_rn(__fmul_rn(__uint_as_float(v[4 * j + 3]), rs), bb.w));
+                reinterpret_cast<float4*>(gp)[j] = o;
+              }
+            }
+          }
+          continue;
+        }
+        // the store issued two chunks ago has finished reading the tile this chunk is written into
+        if (lane == 0) bulk_wait_read1();
+        __syncwarp();
+        uint8_t* hrow = hbuf + (q & 1) * 2048 + lane * 64;
+        tmem_ld_wait();
+        if (col0 < d.k_end) {
+          const float sc = (col0 < d.q_end) ? __fmul_rn(d.q_scale, rs) : rs;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o;
+            rope_pair(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]), rr[j].x, rr[j].y, sc, o.x, o.y);
+            rope_pair(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]), rr[j].z, rr[j].w, sc, o.z, o.w);
+            *reinterpret_cast<uint2*>(hrow + (((j >> 1) ^ sw3) * 16) + (j & 1) * 8) = pack4_bf16(o);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 o = make_float4(__uint_as_float(v[4 * j + 0]) * rs, __uint_as_float(v[4 * j + 1]) * rs,
+                                         __uint_as_float(v[4 * j + 2]) * rs, __uint_as_float(v[4 * j + 3]) * rs);
+            *reinterpret_cast<uint2*>(hrow + (((j >> 1) ^ sw3) * 16) + (j & 1) * 8) = pack4_bf16(o);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (col0 < d.k_end) tma_store_2d(&args.tmO, hbuf + (q & 1) * 2048, col0, m0 + ew * 32);
+          else tma_store_2d(&args.tmO16, hbuf + (q & 1) * 2048, col0 - d.k_end, m0 + ew * 32);
+          bulk_commit();
+        }
+        ++q;
+      }
+    }
+    if (!waited) {              // (a warp without chunks in a ragged tile still takes part in the accumulator hand-over)
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) arrive_tempty(tw, &tempty[as]);
+  }
+  if (lane == 0) bulk_wait0();
+  __syncwarp();
+}
+
 template <int BN, int EPI, int EW, int CG = 1>
 __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_constant__ GemmArgs args) {
   using Cfg = GemmCfg<BN, EW, EPI, CG>;
@@ -384,6 +520,10 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
       tma_prefetch_desc(&args.tmR);
       tma_prefetch_desc(&args.tmO);
       if (d.out_b16) tma_prefetch_desc(&args.tmO16);
+    }
+    if constexpr (EPI == EPI_QKV_TMA) {
+      tma_prefetch_desc(&args.tmO);
+      if (d.v_end > d.k_end) tma_prefetch_desc(&args.tmO16);
     }
   }
   if (warp == W_MMA && lane == 0) {
@@ -503,6 +643,8 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
   } else if (warp < EW) {
    if constexpr (EPI == EPI_RESID_TMA) {
     rt_epilogue<BN, EW, CG>(args, sEpi, rfull, tfull, tempty, tmem_base, warp, lane, tw);
+   } else if constexpr (EPI == EPI_QKV_TMA) {
+    qt_epilogue<BN, EW, CG>(args, sEpi, tfull, tempty, tmem_base, warp, lane, tw);
    } else {
     // ------------------------------------------------------------ epilogue (TMEM -> regs -> smem transpose -> global)
     const int ewi = warp;
@@ -660,12 +802,10 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               const float4 a = bufr[4 * k * EPI_PITCH4];
-              const float sc = rowscale ? sc0 * rsv[4 * k + rsub] : sc0;
+              const float sc = rowscale ? __fmul_rn(sc0, rsv[4 * k + rsub]) : sc0;
               float4 o;
-              o.x = (a.x * cs[k].x - a.y * cs[k].y) * sc;
-              o.y = (a.y * cs[k].x + a.x * cs[k].y) * sc;
-              o.z = (a.z * cs[k].z - a.w * cs[k].w) * sc;
-              o.w = (a.w * cs[k].z + a.z * cs[k].w) * sc;
+              rope_pair(a.x, a.y, cs[k].x, cs[k].y, sc, o.x, o.y);
+              rope_pair(a.z, a.w, cs[k].z, cs[k].w, sc, o.z, o.w);
               if (R.out[k]) {
                 if (d.qk_f32) *reinterpret_cast<float4*>(d.qk_f32 + (size_t)(m0 + ew * 32 + 4 * k + rsub) * d.ldo + col) = o;
                 else *reinterpret_cast<uint2*>(R.out[k] + col * 2) = pack4_bf16(o);
@@ -690,11 +830,11 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) gemm_kernel(const __grid_con
             for (int k = 0; k < 8; ++k) {
               const float4 a0 = bufr[4 * k * EPI_PITCH4];
               const float rs = rowscale ? rsv[4 * k + rsub] : 1.0f;
-              const float e[4] = {a0.x * rs, a0.y * rs, a0.z * rs, a0.w * rs};
+              const float e[4] = {__fmul_rn(a0.x, rs), __fmul_rn(a0.y, rs), __fmul_rn(a0.z, rs), __fmul_rn(a0.w, rs)};
               if (R.out2[k]) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                  if (col + i < d.N) reinterpret_cast<float*>(R.out2[k])[gc + i] = sigmoidf_(e[i] + __ldg(d.hgate_bias + gc + i));
+                  if (col + i < d.N) reinterpret_cast<float*>(R.out2[k])[gc + i] = sigmoidf_(__fadd_rn(e[i], __ldg(d.hgate_bias + gc + i)));
               }
             }
           }
@@ -900,7 +1040,7 @@ static int launch_t(const GemmArgs& a, cudaStream_t st) {
     const int tiles = m_tiles * n_tiles;
     grid = tiles < num_sms() ? tiles : num_sms();
   }
-  static const char* kinds[] = {"gemm_bf16", "gemm_f32", "gemm_geglu", "gemm_resid", "gemm_qkv", "gemm_resid"};
+  static const char* kinds[] = {"gemm_bf16", "gemm_f32", "gemm_geglu", "gemm_resid", "gemm_qkv", "gemm_resid", "gemm_qkv"};
   const double out_cols = (EPI == E2B_EPI_GEGLU) ? a.d.N / 2.0 : a.d.N;
   const double out_bytes = (EPI == E2B_EPI_F32) ? 4.0 : ((EPI == E2B_EPI_RESID || EPI == EPI_RESID_TMA) ? 8.0 : 2.0);
   ProfScope ps(st, kinds[EPI], a.d.M, a.d.N, a.d.K, 2.0 * a.d.M * a.d.N * a.d.K,
@@ -945,6 +1085,8 @@ extern "C" const char* e2b_kernel_last_error(void) { return g_err; }
 extern "C" int e2b_gemm_resid_tma = -1;
 
 extern "C" int e2b_gemm_resid_tma_ew8_max_k = 3072;
+// EPI_QKV (bf16 mode, V as rows) through the row-per-lane / TMA-store epilogue (1, default) or the classic one (0; E2B_QKV_TMA=0)
+extern "C" int e2b_gemm_qkv_tma = -1;
 // CTA-pair (tcgen05 cta_group::2, 256-row tiles) variants for launches with 256-wide column tiles whose tile count fills the 74
 // clusters (E2B_GEMM_CG2=0 switches them off).  tools/bench_gemm_pf.py (AB=pair), profiles/r02_gemm_cta_pair_ab.txt: +8-12 % on the
 // large GEMMs standalone (GEGLU text 1365 -> 1516 TF/s), 122.9 -> 128.4 audio-s/s for the whole C2 step.
@@ -974,6 +1116,10 @@ static void read_env_knobs() {
     const char* e = getenv("E2B_GEMM_PF");
     e2b_gemm_prefetch_kb = e ? atoi(e) : 0;
   }
+  if (e2b_gemm_qkv_tma < 0) {
+    const char* e = getenv("E2B_QKV_TMA");
+    e2b_gemm_qkv_tma = e ? atoi(e) : 1;
+  }
   if (e2b_gemm_cta_pair < 0) {
     const char* e = getenv("E2B_GEMM_CG2");
     e2b_gemm_cta_pair = e ? atoi(e) : 1;
@@ -992,6 +1138,16 @@ extern "C" int e2b_gemm_resid_uses_tma(const e2b_gemm_desc* d) {
   return d->epi == E2B_EPI_RESID && e2b_gemm_resid_tma && d->resid && d->ldo % 4 == 0 && d->ldr % 4 == 0 &&
          !(reinterpret_cast<uintptr_t>(d->out) & 15) && !(reinterpret_cast<uintptr_t>(d->resid) & 15) &&
          (!d->out_b16 || (d->split == 0 && d->ldo_b16 % 8 == 0 && !(reinterpret_cast<uintptr_t>(d->out_b16) & 15)));
+}
+
+// does an EPI_QKV launch of this description take the TMA-store epilogue?  (bf16 outputs, V as plain rows, 16-byte aligned rows)
+static bool qkv_uses_tma(const e2b_gemm_desc* d) {
+  read_env_knobs();
+  const bool has_v = d->v_end > d->k_end, has_gate = d->N > d->v_end;
+  return d->epi == E2B_EPI_QKV && e2b_gemm_qkv_tma && !d->qk_f32 && !d->v_f32 && d->rope && d->ldo % 8 == 0 && !(reinterpret_cast<uintptr_t>(d->out) & 15) &&
+         (!has_v || (d->v_rowmajor && d->vt && d->vt_ld % 8 == 0 && !(reinterpret_cast<uintptr_t>(d->vt) & 15))) &&
+         (!has_gate || (d->hgate && d->hgate_bias && d->hgate_ld % 4 == 0 && (d->N - d->v_end) % 4 == 0 && !(reinterpret_cast<uintptr_t>(d->hgate) & 15) &&
+                        !(reinterpret_cast<uintptr_t>(d->hgate_bias) & 15)));
 }
 
 extern "C" int e2b_gemm_row_parts(const e2b_gemm_desc* d) {
@@ -1069,6 +1225,20 @@ extern "C" int e2b_gemm_launch(const e2b_gemm_desc* d, cudaStream_t stream) {
   if (d->in_row_ss && ((d->epi != E2B_EPI_GEGLU && d->epi != E2B_EPI_QKV) || d->qk_f32 || d->in_row_parts <= 0)) {
     e2b_set_kernel_error("gemm: in_row_ss (norm as a row scale) is for the bf16 GEGLU / QKV epilogues");
     return -1;
+  }
+  if (qkv_uses_tma(d)) {
+    // q | k and v rows leave through the TMA unit: 32 x 32 bf16 boxes, 64-byte swizzle
+    const uint32_t box[2] = {32, 32};
+    const uint64_t dqk[2] = {(uint64_t)d->k_end, (uint64_t)d->M}, sqk[1] = {(uint64_t)d->ldo * 2};
+    if (make_tmap_swizzled(&a.tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d->out, dqk, sqk, box, CU_TENSOR_MAP_SWIZZLE_64B)) return -1;
+    if (d->v_end > d->k_end) {
+      const uint64_t dv[2] = {(uint64_t)(d->v_end - d->k_end), (uint64_t)d->M}, sv[1] = {(uint64_t)d->vt_ld * 2};
+      if (make_tmap_swizzled(&a.tmO16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d->vt, dv, sv, box, CU_TENSOR_MAP_SWIZZLE_64B)) return -1;
+    }
+    const bool ew8q = d->K <= e2b_gemm_ew8_max_k;
+    if (!bn256) return launch_t<128, EPI_QKV_TMA, 4>(a, stream);
+    if (pair) return ew8q ? launch_t<256, EPI_QKV_TMA, 8, 2>(a, stream) : launch_t<256, EPI_QKV_TMA, 4, 2>(a, stream);
+    return ew8q ? launch_t<256, EPI_QKV_TMA, 8>(a, stream) : launch_t<256, EPI_QKV_TMA, 4>(a, stream);
   }
   if (d->row_ss || d->b16_scale) { e2b_set_kernel_error("gemm: row sums / scaled bf16 copy need the TMA residual epilogue (EPI_RESID, 16-byte aligned buffers, no hi/lo split)"); return -1; }
   const bool ew8 = d->K <= e2b_gemm_ew8_max_k;   // small K: epilogue-bound, use 8 epilogue warps + 3 stages
