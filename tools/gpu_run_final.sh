@@ -19,7 +19,7 @@ ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_pe
     --log-file gpurun_out/r02_ncu_launches.csv python tools/prof_forward.py --batch 64 > gpurun_out/r02_ncu_launches.log 2>&1
 python tools/ncu_tensor_share.py gpurun_out/r02_ncu_launches.csv > gpurun_out/r02_ncu_tensor_share.txt 2>&1
 cat gpurun_out/r02_ncu_tensor_share.txt
-# ncu --set full on one layer's kernels (audio stream of layer 0 and the text stream's GEMMs); summary made here, the report stays on the box
-ncu --set full --clock-control none --import-source on -k regex:"gemm_kernel|attention_kernel|dwconv_tma_kernel" -s 14 -c 24 -o /tmp/r02_layer python tools/prof_forward.py --batch 64 > gpurun_out/r02_ncu_full.log 2>&1
-python tools/ncu_summary.py /tmp/r02_layer.ncu-rep 8 > gpurun_out/r02_ncu_layer_summary.txt 2>&1
+# ncu --set full on the HBM-bound front-end / sampler kernels (melspec, guided Euler update, frame windows, condition staging)
+ncu --set full --clock-control none --import-source on -k regex:"melspec_kernel|mel_ranges_kernel|guided_euler_kernel|frame_windows_kernel|roll_expand_kernel" -c 10 -o /tmp/r02_hbm python tools/bench_hbm_kernels.py > gpurun_out/r02_ncu_hbm.log 2>&1
+python tools/ncu_summary.py /tmp/r02_hbm.ncu-rep 6 > gpurun_out/r02_ncu_hbm_kernels_summary.txt 2>&1
 ls -la gpurun_out | tail -30
