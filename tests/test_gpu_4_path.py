@@ -178,6 +178,26 @@ def test_graph_replay_is_bit_identical_to_eager(apg):
     assert not torch.equal(via_graph, eager)
 
 
+@pytest.mark.parametrize('gold', ['tiny_x3.pt', 'shipped_x3.pt'])
+def test_branch_overlap_is_bit_identical_to_one_stream(gold, monkeypatch):
+    """Small batches run the text / frames branches on their own streams beside the audio stream (own scratch buffers, event
+    ordering around the pre-update bf16 copies).  Same kernels, same data: the latents must equal the one-stream schedule bit for
+    bit -- eagerly, while the graph is captured, and replayed."""
+    g, r, cfg, bt = load_gold(gold)
+    d = dev(bt)
+    outs = {}
+    for rows in ('0', '1000000'):
+        monkeypatch.setenv('E2B_OVERLAP_ROWS', rows)       # read when the workspace of a shape is allocated
+        m, _ = build_model(cfg, r['weight_seed'])
+        run = lambda: m.sample(torch.zeros_like(d['y0']), text=d['clip'], lens=d['lens'], duration=d['lens'], steps=r['steps'],
+                               cfg_strength=r['cfg_strength'], remove_parallel_component=False, sway_sampling=True, return_raw_output=True,
+                               context=d['ctx'], context_mask=d['ctx_mask'], frames=d['frames'], noise=d['y0'].clone())
+        outs[rows] = [run(), run(), run()]                 # eager, captured, replayed
+        del m
+    for a in outs['0'] + outs['1000000']:
+        assert torch.equal(a, outs['0'][0])
+
+
 def test_graph_replay_follows_new_lengths_and_context():
     """Clip lengths, context lengths and pass data live in device buffers that set_conditions rewrites: a replayed graph must use
     the new ones (nothing length-dependent may be baked into a captured launch)."""

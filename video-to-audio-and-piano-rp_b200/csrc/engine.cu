@@ -99,6 +99,14 @@ struct e2b_handle {
   float* condm = nullptr;          // [B, n, num_channels] the condition itself, for the final where(cond_mask, cond, out)
   int gam_capacity = 0;
   int pass_flags[8] = {0};
+
+  // Small batches: the text and frames branches of layer l+1 run on their own streams beside the audio stream of layer l (their kernels
+  // do not fill the GPU: one 10 s clip is 13 row tiles).  Each branch then needs its own scratch set.
+  struct Scratch { bf16 *nb = nullptr, *qk = nullptr, *vt = nullptr, *ob = nullptr, *hb = nullptr; float *hg = nullptr, *rss = nullptr; };
+  Scratch scr_t, scr_f;
+  bool overlap = false;            // decided per prepared shape (allocate_workspace)
+  cudaStream_t s_text = nullptr, s_frames = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_tside = nullptr, ev_fside = nullptr, ev_tfa = nullptr, ev_at = nullptr, ev_af = nullptr, ev_audio = nullptr;
 };
 
 namespace {
@@ -308,6 +316,9 @@ void free_workspace(e2b_handle* h) {
   h->gam_capacity = 0;
   h->conditions_set = false;
   h->audio_cond = false;
+  h->overlap = false;
+  h->scr_t = e2b_handle::Scratch();
+  h->scr_f = e2b_handle::Scratch();
 }
 
 // ------------------------------------------------------------------------------------------ gemm descriptor helpers
@@ -479,6 +490,23 @@ int side_stream(e2b_handle* h, float* (&s)[2], bf16* sb, int C, int heads, int i
   return 0;
 }
 
+// The scratch buffers a branch works in: while a ScratchScope with a set is alive, the handle's nb / qk / vt / ob / hb / hg / rss
+// point into that set (launches capture the pointers when they are queued; the host queues one branch at a time).
+struct ScratchScope {
+  e2b_handle* h;
+  e2b_handle::Scratch saved;
+  bool on;
+  ScratchScope(e2b_handle* h_, const e2b_handle::Scratch* set) : h(h_), on(set != nullptr) {
+    if (!on) return;
+    saved.nb = h->nb; saved.qk = h->qk; saved.vt = h->vt; saved.ob = h->ob; saved.hb = h->hb; saved.hg = h->hg; saved.rss = h->rss;
+    h->nb = set->nb; h->qk = set->qk; h->vt = set->vt; h->ob = set->ob; h->hb = set->hb; h->hg = set->hg; h->rss = set->rss;
+  }
+  ~ScratchScope() {
+    if (!on) return;
+    h->nb = saved.nb; h->qk = saved.qk; h->vt = saved.vt; h->ob = saved.ob; h->hb = saved.hb; h->hg = saved.hg; h->rss = saved.rss;
+  }
+};
+
 // Streams x/text/frames (fp32) and xb (bf16 of x) are initialised; gam = time tables for this call.
 int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
   const e2b_config& c = h->cfg;
@@ -492,11 +520,35 @@ int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
   // (e2b_sample / e2b_forward; Transformer.forward with per-item times keeps the rmsnorm kernel)
   const bool fuse = h->fuse_side && gam.bstride == 0;
 
+  if (h->overlap) {                  // fork: the branch streams start after everything already queued on st
+    CU(cudaEventRecord(h->ev_fork, st));
+    CU(cudaStreamWaitEvent(h->s_text, h->ev_fork, 0));
+    CU(cudaStreamWaitEvent(h->s_frames, h->ev_fork, 0));
+  }
   for (int l = 0; l < c.depth; ++l) {
     const LayerW& w = h->L[l];
     e2b::NvtxRange layer_range("e2b.layer");
-    if (side_stream(h, h->text, h->textb, dt, H, h->inner_t, w.t, st, "e2b.text_stream")) return -1;
-    if (side_stream(h, h->frames, h->framesb, df, c.frames_heads, h->inner_f, w.f, st, "e2b.frames_stream")) return -1;
+    // Default: one stream.  Overlap (small batches): text / frames branches on their own streams; layer l+1's branches run beside
+    // the audio stream of layer l.  Ordering: the cross-condition GEMMs read the PRE-update bf16 copies xb / textb / framesb, so
+    //   tfa(l) waits for both branches of layer l;  at(l) / af(l) wait for the audio stream of layer l-1 (xb) and run beside tfa(l);
+    //   the branches of layer l+1 overwrite textb / framesb only after tfa(l) has read them;  the audio stream of layer l
+    //   overwrites xb only after at(l) / af(l) have read it.
+    const bool ov = h->overlap;
+    cudaStream_t st_t = ov ? h->s_text : st, st_f = ov ? h->s_frames : st;
+    {
+      ScratchScope sc(h, ov ? &h->scr_t : nullptr);
+      if (side_stream(h, h->text, h->textb, dt, H, h->inner_t, w.t, st_t, "e2b.text_stream")) return -1;
+    }
+    {
+      ScratchScope sc(h, ov ? &h->scr_f : nullptr);
+      if (side_stream(h, h->frames, h->framesb, df, c.frames_heads, h->inner_f, w.f, st_f, "e2b.frames_stream")) return -1;
+    }
+    if (ov) {
+      CU(cudaEventRecord(h->ev_tside, st_t));
+      CU(cudaEventRecord(h->ev_fside, st_f));
+      CU(cudaStreamWaitEvent(st, h->ev_tside, 0));
+      CU(cudaStreamWaitEvent(st, h->ev_fside, 0));
+    }
 
     // cross condition (all three read the pre-update bf16 copies)
     bf16* xnew_b = (l < c.depth / 2) ? h->skipb[l] : h->xtmpb;
@@ -509,15 +561,30 @@ int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
         d.out_b16 = xnew_b; d.ldo_b16 = ldb(h, dim); d.split = spl(h, dim);
         CK(e2b_gemm_launch(&d, st));
       }
+      if (ov) CU(cudaEventRecord(h->ev_tfa, st));
       if (w.at_w) {
+        if (ov && l > 0) {             // xb of this layer = the audio stream's output of the previous one
+          CU(cudaStreamWaitEvent(st_t, h->ev_audio, 0));
+          CU(cudaStreamWaitEvent(st_f, h->ev_audio, 0));
+        }
         e2b_gemm_desc d = gdesc(h, M, dt, {{h->xb, dim}, {h->textb, dt}}, w.at_w);
         d.epi = E2B_EPI_RESID;
         d.out = h->text[0]; d.ldo = dt; d.resid = h->text[0]; d.ldr = dt;
-        CK(e2b_gemm_launch(&d, st));
+        CK(e2b_gemm_launch(&d, st_t));
         e2b_gemm_desc e = gdesc(h, M, df, {{h->xb, dim}, {h->framesb, df}}, w.af_w);
         e.epi = E2B_EPI_RESID;
         e.out = h->frames[0]; e.ldo = df; e.resid = h->frames[0]; e.ldr = df;
-        CK(e2b_gemm_launch(&e, st));
+        CK(e2b_gemm_launch(&e, st_f));
+        if (ov) {
+          CU(cudaEventRecord(h->ev_at, st_t));
+          CU(cudaEventRecord(h->ev_af, st_f));
+          CU(cudaStreamWaitEvent(st, h->ev_at, 0));
+          CU(cudaStreamWaitEvent(st, h->ev_af, 0));
+        }
+      }
+      if (ov) {
+        CU(cudaStreamWaitEvent(st_t, h->ev_tfa, 0));
+        CU(cudaStreamWaitEvent(st_f, h->ev_tfa, 0));
       }
     }
     // U-Net skip
@@ -601,6 +668,13 @@ int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
       d.out_b16 = h->xb; d.ldo_b16 = ldb(h, dim); d.split = spl(h, dim);
       CK(e2b_gemm_launch(&d, st));
     }
+    if (h->overlap) CU(cudaEventRecord(h->ev_audio, st));
+  }
+  if (h->overlap) {                  // join: the last layer's at / af ran on the branch streams
+    CU(cudaEventRecord(h->ev_tside, h->s_text));
+    CU(cudaEventRecord(h->ev_fside, h->s_frames));
+    CU(cudaStreamWaitEvent(st, h->ev_tside, 0));
+    CU(cudaStreamWaitEvent(st, h->ev_fside, 0));
   }
   return 0;
 }
@@ -727,6 +801,10 @@ extern "C" void e2b_destroy(e2b_handle* h) {
   if (h->gstream) cudaStreamDestroy(h->gstream);
   if (h->gev0) cudaEventDestroy(h->gev0);
   if (h->gev1) cudaEventDestroy(h->gev1);
+  if (h->s_text) cudaStreamDestroy(h->s_text);
+  if (h->s_frames) cudaStreamDestroy(h->s_frames);
+  for (cudaEvent_t e : {h->ev_fork, h->ev_tside, h->ev_fside, h->ev_tfa, h->ev_at, h->ev_af, h->ev_audio})
+    if (e) cudaEventDestroy(e);
   free_workspace(h);
   free_pool(h->wallocs);
   delete h;
@@ -942,6 +1020,33 @@ static int allocate_workspace(e2b_handle* h, int B, int n, int nc, int P) {
   DA(h->sallocs, h->rss, (size_t)RSS_PARTS * M);
   DA(h->sallocs, h->condbf, (size_t)h->Bt * n * c.num_channels * w2);
   DA(h->sallocs, h->condm, (size_t)B * n * c.num_channels);
+  {
+    // branch overlap (E2B_OVERLAP_ROWS: largest row count that takes it, 0 = never).  One clip per call: sample() 162 -> 127 ms; it
+    // still pays at the C2 batch (partial waves and kernel tails of one branch are filled by another: 130.5 -> 132.3 audio-s/s on the
+    // same box, 125.0 -> 128.2 at 16 clips), so the default is every shape; the two extra scratch sets cost 30 KB per row (3 GB at C2).
+    const char* e = getenv("E2B_OVERLAP_ROWS");
+    const long long max_rows = e ? atoll(e) : (1ll << 40);
+    h->overlap = !h->f32 && h->v_rows && (long long)M <= max_rows;
+    if (h->overlap) {
+      struct { e2b_handle::Scratch* s; int C, HDs, heads, inner; } sets[2] = {{&h->scr_t, dt, h->HDt, c.heads, h->inner_t},
+                                                                               {&h->scr_f, df, h->HDf, c.frames_heads, h->inner_f}};
+      for (auto& t : sets) {
+        DA(h->sallocs, t.s->nb, M * t.C);
+        DA(h->sallocs, t.s->qk, M * 2 * t.HDs);
+        DA(h->sallocs, t.s->vt, M * t.HDs);
+        DA(h->sallocs, t.s->ob, M * t.HDs);
+        DA(h->sallocs, t.s->hb, M * t.inner);
+        DA(h->sallocs, t.s->hg, M * t.heads);
+        DA(h->sallocs, t.s->rss, (size_t)RSS_PARTS * M);
+      }
+      if (!h->s_text) {
+        CU(cudaStreamCreateWithFlags(&h->s_text, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->s_frames, cudaStreamNonBlocking));
+        for (cudaEvent_t* ev : {&h->ev_fork, &h->ev_tside, &h->ev_fside, &h->ev_tfa, &h->ev_at, &h->ev_af, &h->ev_audio})
+          CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+      }
+    }
+  }
   h->B = B;                        // last: marks the workspace as complete
   return 0;
 }
