@@ -17,14 +17,20 @@ constexpr int MEL_THREADS = 256;
 constexpr int MEL_FR = 8;        // frames per CTA (one 32-byte output segment per mel row)
 
 // First / one-past-last frequency bin with a non-zero weight, per mel filter (triangular filters touch 3-45 of the 513 bins:
-// the dense [bins x mels] product of the first version spent most of its FMAs on zeros).  One thread per filter, run once per call.
+// the dense [bins x mels] product of the first version spent most of its FMAs on zeros).  One warp per filter (lanes stride over
+// the bins: 17 independent loads per lane instead of 513 dependent ones in one thread, 39 -> ~4 us), run once per call.
 __global__ void mel_ranges_kernel(const float* __restrict__ fb, int nbins, int n_mels, int2* __restrict__ range) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (m >= n_mels) return;
   int lo = nbins, hi = 0;
-  for (int k = 0; k < nbins; ++k)
-    if (fb[(size_t)k * n_mels + m] != 0.f) { lo = min(lo, k); hi = k + 1; }
-  range[m] = make_int2(lo, hi > lo ? hi : lo);
+  for (int k = lane; k < nbins; k += 32)
+    if (fb[(size_t)k * n_mels + m] != 0.f) { lo = min(lo, k); hi = max(hi, k + 1); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) range[m] = make_int2(lo, hi > lo ? hi : lo);
 }
 
 // Two real frames share one complex FFT: z = x1 + i x2 (windowed), Z = FFT(z), and by conjugate symmetry
@@ -152,7 +158,7 @@ extern "C" int e2b_melspec_launch(const float* wav, int B, int nw, int n_fft, in
   const size_t smem = (2 * n_fft + 2 * (n_fft / 2 + 1) + n_mels * MEL_FR) * sizeof(float);
   int2* range = ranges_for(n_mels);
   if (!range) { e2b_set_kernel_error("melspec: filter range table allocation failed"); return -1; }
-  mel_ranges_kernel<<<(n_mels + 127) / 128, 128, 0, stream>>>(fb, n_fft / 2 + 1, n_mels, range);
+  mel_ranges_kernel<<<(n_mels + 3) / 4, 128, 0, stream>>>(fb, n_fft / 2 + 1, n_mels, range);
   static size_t configured_bytes[E2B_MAX_DEVICES] = {0};
   size_t& configured = configured_bytes[e2b_device_slot()];
   if (smem > 48 * 1024 && smem > configured) {
