@@ -385,6 +385,8 @@ def main():
             k['ms'] += r['ms']; k['flops'] += r['flops'] * r['count']; k['bytes'] += r['bytes'] * r['count']; k['launches'] += r['count']
         fwd = dict(flops_per_update=flops_update, ms_per_update_profiled=total_ms, tflops=tf_all, frac_of_sustained=tf_all / pk['sustained'],
                    tensor_kernel_share=sum(r['ms'] for r in tensor_rows) / total_ms,
+                   schedule='one stream: the library switches the three-stream branch overlap off while the event profiler is on, so these '
+                            'are unperturbed per-kernel times (their sum is a few percent above the overlapped step)',
                    by_kind={k: dict(ms=round(v['ms'], 3), share=round(v['ms'] / total_ms, 4),
                                     tflops=round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 1) if v['flops'] else None,
                                     gbs=round(v['bytes'] / (v['ms'] * 1e-3) / 1e9, 1), launches=v['launches'])

@@ -520,7 +520,9 @@ int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
   // (e2b_sample / e2b_forward; Transformer.forward with per-item times keeps the rmsnorm kernel)
   const bool fuse = h->fuse_side && gam.bstride == 0;
 
-  if (h->overlap) {                  // fork: the branch streams start after everything already queued on st
+  // (the per-kernel event profiler wants unperturbed kernel times: one stream while it is on)
+  const bool overlap_now = h->overlap && !e2b_prof_is_on_();
+  if (overlap_now) {                 // fork: the branch streams start after everything already queued on st
     CU(cudaEventRecord(h->ev_fork, st));
     CU(cudaStreamWaitEvent(h->s_text, h->ev_fork, 0));
     CU(cudaStreamWaitEvent(h->s_frames, h->ev_fork, 0));
@@ -533,7 +535,7 @@ int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
     //   tfa(l) waits for both branches of layer l;  at(l) / af(l) wait for the audio stream of layer l-1 (xb) and run beside tfa(l);
     //   the branches of layer l+1 overwrite textb / framesb only after tfa(l) has read them;  the audio stream of layer l
     //   overwrites xb only after at(l) / af(l) have read it.
-    const bool ov = h->overlap;
+    const bool ov = overlap_now;
     cudaStream_t st_t = ov ? h->s_text : st, st_f = ov ? h->s_frames : st;
     {
       ScratchScope sc(h, ov ? &h->scr_t : nullptr);
@@ -668,9 +670,9 @@ int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
       d.out_b16 = h->xb; d.ldo_b16 = ldb(h, dim); d.split = spl(h, dim);
       CK(e2b_gemm_launch(&d, st));
     }
-    if (h->overlap) CU(cudaEventRecord(h->ev_audio, st));
+    if (overlap_now) CU(cudaEventRecord(h->ev_audio, st));
   }
-  if (h->overlap) {                  // join: the last layer's at / af ran on the branch streams
+  if (overlap_now) {                 // join: the last layer's at / af ran on the branch streams
     CU(cudaEventRecord(h->ev_tside, h->s_text));
     CU(cudaEventRecord(h->ev_fside, h->s_frames));
     CU(cudaStreamWaitEvent(st, h->ev_tside, 0));
