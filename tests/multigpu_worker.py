@@ -38,7 +38,10 @@ def main():
         # contiguous partition used by the test holds an even clip, so every batch is padded to the same n
         lens = [n if c % 2 == 0 else n - 5 * (c % 3 + 1) for c in clips]
         assert max(lens) == n
-        bt = synth.batch(clips, n, lens=lens, nc_list=[8 - c % 3 for c in clips], dim_text=cfg['dim_text'], dim=cfg['dim'],
+        # Context lengths: ragged too, but every batch must be padded to the SAME context length (even clips keep 8 tokens): the
+        # reference rotates cross-attention keys with the LAST rows of the rotary table (x-transformers, X3 via oracle/third_party.py),
+        # so a clip's result depends on the padded length of the T5 batch it sits in -- in the reference as in this drop-in.
+        bt = synth.batch(clips, n, lens=lens, nc_list=[8 if c % 2 == 0 else 6 + c % 3 for c in clips], dim_text=cfg['dim_text'], dim=cfg['dim'],
                          d=cfg['num_channels'], live_frames=True)
         d = {k: v.to(dev) for k, v in bt.items()}
         out = m.sample(torch.zeros_like(d['y0']), text=d['clip'], lens=d['lens'], duration=d['lens'], steps=steps, cfg_strength=2.0,

@@ -19,7 +19,7 @@ def _launch(world, arch, clips, n, steps, port):
            '--master-port', str(port), os.path.join(HERE, 'multigpu_worker.py'), arch, str(clips), str(n), str(steps)]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     lines = [l for l in p.stdout.splitlines() if l.startswith('{')]
-    assert p.returncode == 0 and lines, p.stdout[-2000:] + p.stderr[-4000:]
+    assert p.returncode == 0 and lines, p.stdout[-2000:] + p.stderr[-12000:]
     return json.loads(lines[-1])
 
 
