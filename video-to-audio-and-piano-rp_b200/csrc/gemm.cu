@@ -1,15 +1,19 @@
 // tcgen05 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T, bf16 operands, fp32 accumulation in TMEM.
 //
-//   * persistent, warp-specialised CTA (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
-//     warp 2 = TMEM allocator, warps 4-7 = epilogue (one TMEM lane quarter each)
+//   * persistent, warp-specialised CTA: warps 0..EW-1 = epilogue (EW = 4 or 8; one or two per TMEM lane quarter), then one TMA
+//     producer warp, one MMA issuer warp and one TMEM allocator warp (the single-thread roles run warp-uniform, the instruction
+//     under elect_one)
 //   * operands staged by TMA (SWIZZLE_128B boxes of 64 K-elements) through a STAGES-deep mbarrier ring
-//   * 128 x BN accumulator tile, double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
-//     MMAs of tile i+1
-//   * A may be the K-concatenation of up to three tensors (the reference's `pack((audio, text, frames))`
-//     e2_tts_crossatt3.py:693-695 and `torch.cat((x, skip))` :1116) -- the concat tensor is never materialised
+//   * 128 x BN accumulator tile (BN = 128 or 256), double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
+//     MMAs of tile i+1; CG = 2: a CTA pair shares a 256 x 256 tile (tcgen05.mma.cta_group::2, half of the B tile per CTA)
+//   * A may be the K-concatenation of up to nine tensors (the reference's `pack((audio, text, frames))` e2_tts_crossatt3.py:693-695,
+//     `torch.cat((x, skip))` :1116, `proj_in + cond_proj_in`, and the (hi, lo, hi) sources of the fp32 mode) -- never materialised
+//   * a ragged last column tile runs an MMA only as wide as its columns, with its own B box
 //   * fused epilogues: bias, GEGLU (x-transformers FeedForward glu=True), residual + AdaLN-Zero gate + row mask
-//     (e2_tts_crossatt3.py:546-551, 1128-1137), and the QKV epilogue (interleaved RoPE on q/k, q pre-scaling,
-//     transposed V store for the attention kernel, sigmoid value-head gate).
+//     (e2_tts_crossatt3.py:546-551, 1128-1137), QKV (interleaved RoPE on q/k, q pre-scaling, V rows, sigmoid value-head gate).
+//     Classic form: transpose each 32 x 32 chunk through shared memory for coalesced global accesses.  Row-per-lane forms
+//     (rt_epilogue, qt_epilogue): a lane keeps the accumulator row tcgen05.ld gives it, residual / results move by TMA, and the
+//     RMSNorm of the value just produced becomes row sums + a scaled bf16 copy for the consuming GEMM (norm as a row scale).
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
