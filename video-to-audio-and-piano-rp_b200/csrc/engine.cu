@@ -100,8 +100,9 @@ struct e2b_handle {
   int gam_capacity = 0;
   int pass_flags[8] = {0};
 
-  // Small batches: the text and frames branches of layer l+1 run on their own streams beside the audio stream of layer l (their kernels
-  // do not fill the GPU: one 10 s clip is 13 row tiles).  Each branch then needs its own scratch set.
+  // The text and frames branches of layer l+1 run on their own streams beside the audio stream of layer l (at small batches their
+  // kernels do not fill the GPU -- one 10 s clip is 13 row tiles -- and at large ones partial waves and tails overlap).  Each branch
+  // then needs its own scratch set.
   struct Scratch { bf16 *nb = nullptr, *qk = nullptr, *vt = nullptr, *ob = nullptr, *hb = nullptr; float *hg = nullptr, *rss = nullptr; };
   Scratch scr_t, scr_f;
   bool overlap = false;            // decided per prepared shape (allocate_workspace)
@@ -530,7 +531,7 @@ int forward_core(e2b_handle* h, GamRef gam, cudaStream_t st) {
   for (int l = 0; l < c.depth; ++l) {
     const LayerW& w = h->L[l];
     e2b::NvtxRange layer_range("e2b.layer");
-    // Default: one stream.  Overlap (small batches): text / frames branches on their own streams; layer l+1's branches run beside
+    // One stream, or (h->overlap, the default in bf16 mode) text / frames branches on their own streams: layer l+1's branches run beside
     // the audio stream of layer l.  Ordering: the cross-condition GEMMs read the PRE-update bf16 copies xb / textb / framesb, so
     //   tfa(l) waits for both branches of layer l;  at(l) / af(l) wait for the audio stream of layer l-1 (xb) and run beside tfa(l);
     //   the branches of layer l+1 overwrite textb / framesb only after tfa(l) has read them;  the audio stream of layer l
