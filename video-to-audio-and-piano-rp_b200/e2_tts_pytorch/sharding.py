@@ -31,3 +31,21 @@ def gather_latents(local: torch.Tensor, num_clips: int, group=None) -> torch.Ten
     out = local.new_empty(world * bmax, *local.shape[1:])
     dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
     return torch.cat([out[r * bmax:r * bmax + sizes[r]] for r in range(world)])
+
+
+def pad_context_to_common_length(context: torch.Tensor, context_mask: torch.Tensor, group=None):
+    """Pad a rank's T5 context batch `[B_local, nc_local, d]` (+ mask `[B_local, nc_local]`) to the longest context of ALL ranks.
+
+    The reference rotates cross-attention keys with the LAST `nc` rows of the rotary table (x-transformers
+    `apply_rotary_pos_emb`: `freqs[:, -seq_len:]`, restated in oracle/third_party.py), so a clip's latent depends on the padded
+    length of the context batch it is sampled with -- in the reference as in this drop-in.  A sharded run therefore equals the
+    one-process run per clip only if every shard pads to the same length; this helper makes that so with one MAX all-reduce.
+    """
+    nc = torch.tensor([context.shape[1]], dtype=torch.int64, device=context.device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(nc, op=dist.ReduceOp.MAX, group=group)
+    pad = int(nc.item()) - context.shape[1]
+    if pad > 0:
+        context = torch.cat([context, context.new_zeros(context.shape[0], pad, context.shape[2])], dim=1)
+        context_mask = torch.cat([context_mask, context_mask.new_zeros(context_mask.shape[0], pad)], dim=1)
+    return context, context_mask
